@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the wekua dense-BLAS hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n SIZE] [--quick]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs 4/5): f32 GEMM, C = A.B (NN), square N = 32768, rows of A and C sharded over the
+N GPUs of the box (N = 1: the whole product on one GPU), synthetic U[-1,1) matrices from the reference's own
+counter-based PRNG (seeds 42/43).  One step = one blas.gemm over the resident operands; `value` = 2*N^3*steps /
+time, whole job, CUDA-event timed on the queue's stream, max over ranks.  `e2e` is the same product through the
+public API from HOST buffers (pinned H2D of A and B and D2H of C inside the timed region).  The `also` list carries
+the other configs the metric names (f32/f64 GEMM N = 16384, f32/f64 axpy on 2^28 elements) with their own rooflines.
+
+--impl reference times the reference's CPU implementation of the same product (the C restatement of
+gemm_pack.cl + gemm_nxn_pack.cl built -O3 with OpenMP, all host cores) on a bounded sample (N = 2048 by default).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------ peaks
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx, self.lines, self.proc = device_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1])
+                mx = float(f[2])
+            except ValueError:
+                continue
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: take everything we saw
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def ev_record(wk, pipe):
+    ev = C.c_void_p()
+    wk.capi.check(wk.capi.lib().wk_event_record(pipe.q, C.byref(ev)))
+    return ev
+
+
+def ev_ms(wk, a, b):
+    ms = C.c_float()
+    wk.capi.check(wk.capi.lib().wk_event_wait(b))
+    wk.capi.check(wk.capi.lib().wk_event_elapsed_ms(a, b, C.byref(ms)))
+    return float(ms.value)
+
+
+def timed(wk, pipe, fn, steps, warmup, barrier=None):
+    """W untimed steps, then exactly K steps bracketed by sync (+ barrier) on both sides; device time via events"""
+    for _ in range(warmup):
+        fn()
+    pipe.wait_and_cleanup()
+    if barrier:
+        barrier()
+    t0 = time.time()
+    l0 = wk.capi.launch_count()
+    e0 = ev_record(wk, pipe)
+    for _ in range(steps):
+        fn()
+    e1 = ev_record(wk, pipe)
+    ms = ev_ms(wk, e0, e1)
+    pipe.wait_and_cleanup()
+    launches = wk.capi.launch_count() - l0
+    if barrier:
+        barrier()
+    t1 = time.time()
+    for e in (e0, e1):
+        wk.capi.lib().wk_event_release(e)
+    return ms, launches, t0, t1
+
+
+def pinned_array(wk, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    wk.capi.check(wk.capi.lib().wk_host_alloc(n, C.byref(p)))
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_gemm(n, dtype, steps, warmup, vw_f32=None):
+    """the restated reference CPU path: PackedTensors + gemm_pack.cl x2 + gemm_nxn_pack.cl per call
+    (benchmark/gemm.zig:150-204 re-packs on every call), -O3, OpenMP over work-items, all host cores."""
+    from oracle import pyoracle as o
+
+    fast = True
+    lib = o.lib(fast=fast)
+    if vw_f32 is None:
+        vw_f32 = 16 if o._cpu_has("avx512f") else 8
+    dev = o.device("cpu", vw_f32)
+    a = o.OTensor(dev, dtype, (n, n), fast=fast).uniform(42, -1, 1)
+    b = o.OTensor(dev, dtype, (n, n), fast=fast).uniform(43, -1, 1)
+    c = o.OTensor(dev, dtype, (n, n), fast=fast)
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        o.gemm(None, a, 0, b, 0, None, c, packed=True, fast=fast)
+        if i >= warmup:
+            times.append(time.perf_counter() - t)
+    sec = float(np.mean(times))
+    return {"tflops": 2.0 * n ** 3 / sec / 1e12, "sec_per_call": sec, "cores": int(lib.wko_num_threads()), "n": n,
+            "vw": vw_f32, "tile": 2 << c.layout.gemm_algorithm}
+
+
+def cpu_reference_axpy(n, dtype, reps=3):
+    from oracle import pyoracle as o
+
+    dev = o.device("cpu", 16 if o._cpu_has("avx512f") else 8)
+    x = o.OTensor(dev, dtype, (n,), fast=True).uniform(42)
+    y = o.OTensor(dev, dtype, (n,), fast=True).uniform(43)
+    o.axpy(x, 0.5, y, fast=True)
+    t = time.perf_counter()
+    for _ in range(reps):
+        o.axpy(x, 0.5, y, fast=True)
+    sec = (time.perf_counter() - t) / reps
+    return 3.0 * n * np.dtype(dtype).itemsize / sec / 1e9
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n
+    r = cpu_reference_gemm(n, np.float32, args.steps, max(args.warmup, 1))
+    sample = (f"f32 NN GEMM N={n} (a {n}^3 sub-problem of the N={args.n} workload), restated gemm_pack.cl + "
+              f"gemm_nxn_pack.cl, {r['tile']}x{r['tile']} tiles, vector width {r['vw']}, re-packed every call")
+    line = {
+        "impl": "reference", "metric": "gemm_f32_tflops", "value": r["tflops"], "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_call"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"f32 GEMM NN N={args.n} row-sharded over {args.gpus} GPU(s)", "sample_n": n},
+        "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def gemm_roofline(tflops, dtype, peaks, sustained, traffic=None):
+    bf16 = peaks["bf16_tflops_sustained" if sustained else "bf16_tflops"]
+    if dtype == "f32":
+        peak = bf16 / 2.0 / 3.0
+        basis = (f"{peaks['_source']} cuBLAS bf16 {'sustained' if sustained else 'burst'} {bf16:.0f} TF/s / 2 (tf32 rate) / 3 "
+                 "(3xTF32 passes per useful flop)")
+    else:
+        peak = 40.0
+        basis = "B200 FP64 tensor-core spec 40 TF/s (no measured FP64 denominator in MEASURED_PEAKS.json)"
+    return {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+            "traffic": traffic, "peak_basis": basis}
+
+
+def hbm_roofline(gbs, peaks, traffic=None):
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": traffic, "peak_basis": f"{peaks['_source']} copy bandwidth"}
+
+
+def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks):
+    """benchmark/axpy.zig:119-162: alternating axpy(x, a, y) / axpy(y, a, x) on N-element vectors"""
+    x = wk.Tensor.alloc(ctx, pipe, (n,), dtype)
+    y = wk.Tensor.alloc(ctx, pipe, (n,), dtype)
+    wk.tensor.random.uniform(pipe, x, 42)
+    wk.tensor.random.uniform(pipe, y, 43)
+    state = {"i": 0}
+    alphas = np.random.default_rng(1234).uniform(-1, 1, 64) / np.sqrt(2)  # |alpha| < 1 keeps values finite
+
+    def step():
+        i = state["i"]
+        a = float(alphas[i % 64])
+        if i % 2 == 0:
+            wk.blas.axpy(pipe, x, a, y)
+        else:
+            wk.blas.axpy(pipe, y, a, x)
+        state["i"] = i + 1
+
+    ms, launches, _, _ = timed(wk, pipe, step, steps, warmup)
+    bytes_per = 3.0 * n * np.dtype(dtype).itemsize
+    gbs = bytes_per * steps / (ms * 1e-3) / 1e9
+    x.release(pipe)
+    y.release(pipe)
+    name = "f32" if np.dtype(dtype) == np.float32 else "f64"
+    return {"metric": f"axpy_{name}_gbs", "value": gbs, "unit": "GB/s", "ms_per_step": ms / steps, "dtype": name,
+            "config": {"workload": f"{name} axpy, 2^{int(np.log2(n))} elements, alternating x/y (benchmark/axpy.zig)",
+                       "l2": "inputs_exceed_l2"},
+            "gpu_launches": launches, "roofline": hbm_roofline(gbs, peaks)}
+
+
+def bench_gemm_single(wk, ctx, pipe, dtype, n, steps, warmup, peaks, op_a=0, op_b=0):
+    a = wk.Tensor.alloc(ctx, pipe, (n, n), dtype)
+    b = wk.Tensor.alloc(ctx, pipe, (n, n), dtype)
+    c = wk.Tensor.alloc(ctx, pipe, (n, n), dtype)
+    wk.tensor.random.uniform(pipe, a, 42, -1, 1)
+    wk.tensor.random.uniform(pipe, b, 43, -1, 1)
+    ms, launches, _, _ = timed(wk, pipe, lambda: wk.blas.gemm(pipe, None, a, op_a, b, op_b, None, c), steps, warmup)
+    tf = 2.0 * n ** 3 * steps / (ms * 1e-3) / 1e12
+    for t in (a, b, c):
+        t.release(pipe)
+    name = "f32" if np.dtype(dtype) == np.float32 else "f64"
+    return {"metric": f"gemm_{name}_tflops", "value": tf, "unit": "TFLOP/s", "ms_per_step": ms / steps, "dtype": name,
+            "config": {"workload": f"{name} GEMM {'NT'[op_a]}{'NT'[op_b]} N={n}, 1 GPU", "l2": "inputs_exceed_l2"},
+            "gpu_launches": launches, "roofline": gemm_roofline(tf, name, peaks, sustained=True)}
+
+
+def run_ours(args):
+    import torch  # plumbing only: torch.distributed rendezvous / barrier / max-reduce, never on the compute path
+
+    import wekua_b200 as wk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
+        args.gpus = world
+    peaks = measured_peaks()
+    ctx = wk.Context.init([local_rank])
+    pipe = wk.Pipeline.init(ctx.command_queues[0])
+    N = args.n
+    g = world
+    rows = N // g  # BASELINE config 5: contiguous row blocks of A and C, B replicated
+    row0 = rank * rows
+    if rank == g - 1:
+        rows = N - row0
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- resident operands: A row block, full B, full C (the gather target)
+    dt = np.float32
+    a = wk.Tensor.alloc(ctx, pipe, (rows, N), dt)
+    b = wk.Tensor.alloc(ctx, pipe, (N, N), dt)
+    c_full = wk.Tensor.alloc(ctx, pipe, (N, N), dt)
+    c_blk = wk.Tensor.wrap(ctx, pipe, (rows, N), dt, c_full.buffer + row0 * c_full.row_pitch * 4)
+    # reference PRNG (uniform.cl); every rank seeds its own row block of A, B is identical everywhere
+    wk.tensor.random.uniform(pipe, a, 42 + 1000 * rank, -1, 1)
+    wk.tensor.random.uniform(pipe, b, 43, -1, 1)
+    pipe.wait_and_cleanup()
+
+    gather = args.gather if world > 1 else "none"
+    c_torch = None
+    if gather == "nccl":
+        class _Cai:
+            __cuda_array_interface__ = {"shape": (N * c_full.row_pitch,), "typestr": "<f4", "data": (c_full.buffer, False),
+                                        "version": 3}
+        c_torch = torch.as_tensor(_Cai(), device=f"cuda:{local_rank}")
+
+    def step():
+        wk.blas.gemm(pipe, None, a, 0, b, 0, None, c_blk)
+        if gather == "nccl":
+            pipe.command_queue.finish()
+            chunk = (N // g) * c_full.row_pitch
+            torch.distributed.all_gather_into_tensor(c_torch[: chunk * g], c_torch[rank * chunk:(rank + 1) * chunk])
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, t0, t1 = timed(wk, pipe, step, args.steps, args.warmup, barrier)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=f"cuda:{local_rank}", dtype=torch.int64)
+        torch.distributed.all_reduce(lt)
+        launches = int(lt.item())
+    flops = 2.0 * N * N * N
+    tflops = flops * args.steps / (ms * 1e-3) / 1e12
+    per_gpu_tflops = tflops / g
+
+    # ---------------- e2e: same product through the public API from HOST buffers (pinned), copies inside the region
+    e2e = None
+    if not args.no_e2e:
+        ha, pa = pinned_array(wk, (rows, N), dt)
+        hb, pb = pinned_array(wk, (N, N), dt)
+        hc, pc = pinned_array(wk, (rows, N), dt)
+        ha[:] = 0.5
+        hb[:] = 0.25
+
+        def e2e_step():
+            wk.tensor.memory.read_from_buffer(pipe, a, ha)
+            wk.tensor.memory.read_from_buffer(pipe, b, hb)
+            wk.blas.gemm(pipe, None, a, 0, b, 0, None, c_blk)
+            wk.tensor.memory.write_to_buffer(pipe, c_blk, hc.reshape(-1))
+
+        e_steps = max(1, min(args.steps, 3))
+        ems, _, _, _ = timed(wk, pipe, e2e_step, e_steps, 1, barrier)
+        if world > 1:
+            t = torch.tensor([ems], device=f"cuda:{local_rank}", dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": flops * e_steps / (ems * 1e-3) / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int((rows * N + N * N) * 4 * g), "d2h_bytes_per_step": int(N * N * 4),
+               "steps": e_steps, "ms_per_step": ems / e_steps}
+        for p in (pa, pb, pc):
+            wk.capi.lib().wk_host_free(p)
+    for t_ in (a, b, c_full):
+        t_.release(pipe)
+
+    # ---------------- secondary configs + cpu baseline (rank 0, N = 1 only)
+    also, cpu = [], None
+    if world == 1 and not args.quick:
+        s2 = max(3, min(args.steps, 10))
+        also.append(bench_gemm_single(wk, ctx, pipe, np.float32, 16384, s2, 3, peaks))
+        also.append(bench_gemm_single(wk, ctx, pipe, np.float64, 16384 if not args.small else 4096, max(3, s2 // 2), 3, peaks))
+        also.append(bench_axpy(wk, ctx, pipe, np.float32, 1 << 28, 50, 5, peaks))
+        also.append(bench_axpy(wk, ctx, pipe, np.float64, 1 << 28, 50, 5, peaks))
+    if world == 1 and rank == 0 and not args.no_cpu:
+        r = cpu_reference_gemm(args.ref_n, np.float32, 3, 1)
+        cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["cores"], "kind": "port",
+               "sample": (f"f32 NN GEMM N={args.ref_n} sub-problem, restated gemm_pack.cl + gemm_nxn_pack.cl "
+                          f"({r['tile']}x{r['tile']} tiles, vw {r['vw']}), OpenMP, {r['sec_per_call']:.2f} s/call"),
+               "axpy_f32_gbs": cpu_reference_axpy(1 << 26, np.float32)}
+
+    if rank == 0:
+        line = {
+            "metric": "gemm_f32_tflops", "value": tflops, "unit": "TFLOP/s", "n_gpus": g, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"f32 GEMM NN N={N}, rows of A/C sharded over {g} GPU(s), B replicated "
+                                   f"(BASELINE config 5); gather={gather}",
+                       "N": N, "parallelism": f"rowshard{g}", "l2": "inputs_exceed_l2", "arith": "3xTF32 tcgen05, fp32 accumulate"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True),
+            "cpu_baseline": cpu, "also": also,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--ref-n", type=int, default=4096, dest="ref_n")
+    ap.add_argument("--gather", default="nccl", choices=["none", "nccl", "fused"])
+    ap.add_argument("--quick", action="store_true", help="headline line only (no secondary configs)")
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

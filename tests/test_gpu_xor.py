@@ -1,0 +1,62 @@
+"""-m gpu: BASELINE config 3 -- examples/xor_neural_network.zig end to end through the CUDA backend
+(Linear + Sigmoid + MSE + GD, 300 steps, batch 4), step-by-step against the op-by-op oracle run."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import gpu_helpers as gh
+from tests.xor_reference import INPUTS, TARGETS, OracleXor
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(wk, ctx, pipe, dtype, seeds, fused):
+    nn = wk.nn
+    inputs = wk.Tensor.alloc(ctx, pipe, (4, 2), dtype)
+    expected = wk.Tensor.alloc(ctx, pipe, (4, 1), dtype)
+    wk.tensor.memory.read_from_buffer(pipe, inputs, INPUTS.astype(dtype))
+    wk.tensor.memory.read_from_buffer(pipe, expected, TARGETS.astype(dtype))
+    seq = nn.Sequential.init()
+    act = nn.Sigmoid.init()
+    seq.append(nn.Linear.init(ctx, pipe, 2, 10, act, dtype=dtype, seed=seeds[0], fused=fused))
+    seq.append(nn.Linear.init(ctx, pipe, 10, 1, act, dtype=dtype, seed=seeds[1], fused=fused))
+    layers = seq.layer()
+    cache = nn.Cache.init(ctx, pipe, 4, [layers])
+    opt = nn.GD.init(None, lr=1)
+    return inputs, expected, seq, layers, cache, opt
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("fused", [False, True])
+def test_xor_training_matches_oracle(oracle, dtype, fused):
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    seeds = (42, 43)
+    inputs, expected, seq, layers, cache, opt = _build(wk, ctx, pipe, dtype, seeds, fused)
+    ref = OracleXor(oracle, gh.oracle_dev(oracle), dtype, seeds)
+    # same PRNG on both sides: initial weights must agree bit for bit (uniform.cl restated on both)
+    for lin, W in zip(seq.layers, ref.W):
+        np.testing.assert_array_equal(gh.to_np(lin.weights[0]), W.to_host())
+    layer_cache = cache.get_layer_cache(0)
+    eps = np.finfo(dtype).eps
+    for it in range(300):
+        output = layers.forward(pipe, inputs, layer_cache)
+        wk.nn.mse(pipe, output, expected, cache, calculate_derivative=True)
+        layers.backward(pipe, layer_cache, inputs, None)
+        opt.step(pipe, cache)
+        ref.step()
+        if it in (0, 1, 9, 99, 299):
+            # exp() differs by ulps between CUDA and glibc; the error compounds slowly over GD steps
+            rtol = eps * 64 * (it + 1)
+            for lin, W, b in zip(seq.layers, ref.W, ref.b):
+                np.testing.assert_allclose(gh.to_np(lin.weights[0]), W.to_host(), rtol=rtol, atol=rtol)
+                np.testing.assert_allclose(gh.to_np(lin.bias[0]), b.to_host(), rtol=rtol, atol=rtol)
+    out = gh.to_np(layers.forward(pipe, inputs, layer_cache)).reshape(-1)
+    np.testing.assert_allclose(out, ref.forward().to_host().reshape(-1), rtol=1e-3, atol=1e-4)
+    assert np.all(np.abs(out - TARGETS.reshape(-1)) < 0.2), out  # it learned XOR
+    err = wk.nn.mse(pipe, layers.forward(pipe, inputs, layer_cache), expected, cache, calculate_derivative=False, want_error=True)
+    assert 0 <= float(err) < 0.05 and math.isfinite(float(err))
+    opt.deinit(pipe)
+    cache.deinit(pipe)
+    seq.deinit(pipe)

@@ -1,0 +1,608 @@
+// elementwise.cu -- the HBM-bound streaming kernels: axpy / scal / hadamard / unary math / activations and
+// their derivatives / bias / mse / optimizers / fill / uniform / identity / transpose.
+//
+// One generic kernel template does the streaming: every thread moves 128-bit vectors, UNROLL independent
+// vectors per pointer are in flight before the first use (memory-level parallelism, guideline 7/13), the grid
+// is a multiple of the SM count and grid-strides over the buffer.  Read-only operands use the non-coherent
+// path with L1 no-allocate; in/out operands use L1 no-allocate loads and plain stores.
+//
+// Reference kernels replaced: src/blas/kernels/axpy.cl, src/math/kernels/{dot,trig}.cl,
+// src/nn/activation/kernels/{sigmoid,tanh}.cl, src/nn/layer/kernels/bias.cl, src/nn/loss/kernels/mse.cl,
+// src/nn/optimizers/kernels/{gdm,adagrad,rmsprop}.cl, src/tensor/kernels/{fill,identity,transpose}.cl,
+// src/tensor/random/kernels/uniform.cl.
+#include <float.h>
+#include <math.h>
+
+#include <limits>
+
+#include "common.cuh"
+
+namespace wk {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kCtasPerSm = 8;
+
+template <int NP> struct Ptrs { void *p[NP]; };
+
+__device__ __forceinline__ uint4 ld_ro(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_rw(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// F: struct with  static constexpr unsigned kRead, kWrite (bit i = pointer i);
+//                 __device__ void operator()(T (&v)[NP], uint64_t idx) const   (idx = element index)
+template <typename T, int NP, typename F>
+__global__ void __launch_bounds__(kThreads) map_vec_kernel(Ptrs<NP> ptrs, uint64_t n, F f) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    union Pack { uint4 u; T e[VEC]; };
+    const uint64_t n_vec = n / VEC;
+    const uint64_t chunk = (uint64_t)kThreads * kUnroll;
+    for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < n_vec; base += (uint64_t)gridDim.x * chunk) {
+        Pack reg[NP][kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_vec) {
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    if (F::kRead & (1u << p)) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(ptrs.p[p]) + vi;
+                        reg[p][u].u = (F::kWrite & (1u << p)) ? ld_rw(src) : ld_ro(src);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_vec) {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    T v[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) v[p] = reg[p][u].e[e];
+                    f(v, vi * VEC + e);
+#pragma unroll
+                    for (int p = 0; p < NP; p++) reg[p][u].e[e] = v[p];
+                }
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (F::kWrite & (1u << p)) st_na(reinterpret_cast<uint4 *>(ptrs.p[p]) + vi, reg[p][u].u);
+            }
+        }
+    }
+    // tail: fewer than VEC elements
+    if (blockIdx.x == 0) {
+        const uint64_t i = n_vec * VEC + threadIdx.x;
+        if (i < n) {
+            T v[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                if (F::kRead & (1u << p)) v[p] = reinterpret_cast<const T *>(ptrs.p[p])[i];
+            f(v, i);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                if (F::kWrite & (1u << p)) reinterpret_cast<T *>(ptrs.p[p])[i] = v[p];
+        }
+    }
+}
+
+// scalar fallback (unaligned pointers)
+template <typename T, int NP, typename F>
+__global__ void __launch_bounds__(kThreads) map_scalar_kernel(Ptrs<NP> ptrs, uint64_t n, F f) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+        T v[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (F::kRead & (1u << p)) v[p] = reinterpret_cast<const T *>(ptrs.p[p])[i];
+        f(v, i);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (F::kWrite & (1u << p)) reinterpret_cast<T *>(ptrs.p[p])[i] = v[p];
+    }
+}
+
+// pitched [depth, rows, cols] variant (logical region of padded tensors): pointer p uses pitches rp[p]/sp[p]
+template <int NP> struct Pitches { uint64_t rp[NP], sp[NP]; };
+template <typename T, int NP, typename F>
+__global__ void __launch_bounds__(kThreads) map_pitched_kernel(Ptrs<NP> ptrs, Pitches<NP> pit, uint64_t depth,
+                                                                uint64_t rows, uint64_t cols, F f) {
+    const uint64_t n_rows = depth * rows;
+    for (uint64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        const uint64_t d = r / rows, j = r - d * rows;
+        for (uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x; k < cols; k += (uint64_t)gridDim.x * kThreads) {
+            T v[NP];
+            uint64_t off[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                off[p] = d * pit.sp[p] + j * pit.rp[p] + k;
+                if (F::kRead & (1u << p)) v[p] = reinterpret_cast<const T *>(ptrs.p[p])[off[p]];
+            }
+            f(v, off[0]);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                if (F::kWrite & (1u << p)) reinterpret_cast<T *>(ptrs.p[p])[off[p]] = v[p];
+        }
+    }
+}
+
+template <typename T, int NP, typename F>
+static int32_t launch_map(wk_queue *q, Ptrs<NP> ptrs, uint64_t n, F f) {
+    if (n == 0) return WK_OK;
+    bool aligned = true;
+    for (int p = 0; p < NP; p++) {
+        if (!ptrs.p[p]) {
+            set_error("null buffer");
+            return WK_ERR_INVALID_BUFFER;
+        }
+        aligned &= aligned16(ptrs.p[p]);
+    }
+    const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+    if (aligned) {
+        constexpr int VEC = 16 / (int)sizeof(T);
+        uint64_t blocks = (n / VEC + (uint64_t)kThreads * kUnroll - 1) / ((uint64_t)kThreads * kUnroll);
+        if (blocks == 0) blocks = 1;
+        if (blocks > cap) blocks = cap;
+        map_vec_kernel<T, NP, F><<<(unsigned)blocks, kThreads, 0, q->stream>>>(ptrs, n, f);
+    } else {
+        uint64_t blocks = (n + kThreads - 1) / kThreads;
+        if (blocks > cap) blocks = cap;
+        map_scalar_kernel<T, NP, F><<<(unsigned)blocks, kThreads, 0, q->stream>>>(ptrs, n, f);
+    }
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
+
+// [depth, rows, cols] with pitches: collapses to the dense 1-D kernel when every operand is contiguous
+template <typename T, int NP, typename F>
+static int32_t launch_map3d(wk_queue *q, Ptrs<NP> ptrs, Pitches<NP> pit, uint64_t depth, uint64_t rows, uint64_t cols,
+                            F f) {
+    if (depth == 0 || rows == 0 || cols == 0) return WK_ERR_INVALID_VALUE;
+    bool dense = true;
+    for (int p = 0; p < NP; p++) {
+        if (!ptrs.p[p]) {
+            set_error("null buffer");
+            return WK_ERR_INVALID_BUFFER;
+        }
+        const bool row_dense = (rows == 1) || (pit.rp[p] == cols);
+        const bool slice_dense = (depth == 1) || (pit.sp[p] == rows * cols && row_dense);
+        dense &= row_dense && slice_dense;
+    }
+    if (dense) return launch_map<T, NP, F>(q, ptrs, depth * rows * cols, f);
+    uint64_t gx = (cols + kThreads - 1) / kThreads;
+    if (gx > 1024) gx = 1024;
+    uint64_t gy = depth * rows;
+    if (gy > 65535) gy = 65535;
+    map_pitched_kernel<T, NP, F><<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, q->stream>>>(ptrs, pit, depth, rows,
+                                                                                              cols, f);
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ functors
+template <typename T, int MODE>  // MODE 0: y += x, 1: y += alpha*x, 2: y -= x  (axpy.cl:55-65)
+struct AxpyF {
+    static constexpr unsigned kRead = 3, kWrite = 2;
+    typename Acc<T>::type alpha;
+    __device__ __forceinline__ void operator()(T (&v)[2], uint64_t) const {
+        using A = typename Acc<T>::type;
+        const A x = to_acc<T>(v[0]), y = to_acc<T>(v[1]);
+        if (MODE == 1) v[1] = from_acc<T>((A)(y + alpha * x));
+        else if (MODE == 2) v[1] = from_acc<T>((A)(y - x));
+        else v[1] = from_acc<T>((A)(y + x));
+    }
+};
+
+template <typename T> struct ScalF {  // old_kernels/scal.cl:3-20
+    static constexpr unsigned kRead = 1, kWrite = 1;
+    typename Acc<T>::type alpha;
+    __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const {
+        v[0] = from_acc<T>((typename Acc<T>::type)(to_acc<T>(v[0]) * alpha));
+    }
+};
+
+template <typename T> struct HadamardF {  // dot.cl:33
+    static constexpr unsigned kRead = 3, kWrite = 1;
+    __device__ __forceinline__ void operator()(T (&v)[2], uint64_t) const {
+        v[0] = from_acc<T>((typename Acc<T>::type)(to_acc<T>(v[0]) * to_acc<T>(v[1])));
+    }
+};
+
+template <typename T> struct FillF {  // fill.cl:11-16
+    static constexpr unsigned kRead = 0, kWrite = 1;
+    T value;
+    __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const { v[0] = value; }
+};
+
+__device__ __forceinline__ float wk_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ double wk_sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
+    static constexpr unsigned kRead = 1, kWrite = 1;
+    __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const {
+        const T x = v[0];
+        if (OP == WK_OP_SIN) v[0] = sin(x);
+        else if (OP == WK_OP_COS) v[0] = cos(x);
+        else if (OP == WK_OP_TAN) v[0] = tan(x);
+        else if (OP == WK_OP_SINH) v[0] = sinh(x);
+        else if (OP == WK_OP_COSH) v[0] = cosh(x);
+        else if (OP == WK_OP_TANH) v[0] = tanh(x);
+        else v[0] = wk_sigmoid(x);
+    }
+};
+
+template <typename T, int ACT> struct ActDevF {  // sigmoid.cl:31-32 (ACT=1), tanh.cl:16-17 (ACT=2)
+    static constexpr unsigned kRead = 1, kWrite = 2;
+    __device__ __forceinline__ void operator()(T (&v)[2], uint64_t) const {
+        const T y = v[0];
+        v[1] = ACT == WK_ACT_SIGMOID ? y * ((T)1 - y) : (T)1 - y * y;
+    }
+};
+
+// fused: derivative (optionally stored) and sensitivity *= derivative  (linear.zig:608-613)
+template <typename T, int ACT, bool STORE> struct ActBackwardF {
+    static constexpr unsigned kRead = 1 | 4, kWrite = (STORE ? 2 : 0) | 4;
+    __device__ __forceinline__ void operator()(T (&v)[3], uint64_t) const {
+        const T y = v[0];
+        const T d = ACT == WK_ACT_SIGMOID ? y * ((T)1 - y) : (ACT == WK_ACT_TANH ? (T)1 - y * y : (T)1);
+        if (STORE) v[1] = d;
+        v[2] = v[2] * d;
+    }
+};
+
+template <typename T, bool DEV> struct MseF {  // mse.cl:28-33: v = {output, expected, error, dev}
+    static constexpr unsigned kRead = 3, kWrite = 4 | (DEV ? 8 : 0);
+    __device__ __forceinline__ void operator()(T (&v)[4], uint64_t) const {
+        const T err = v[1] - v[0];
+        v[2] = err * err;
+        if (DEV) v[3] = -(T)2 * err;
+    }
+};
+
+template <typename T> struct GdmF {  // gdm.cl:28-31: v = {x, g, velocity}
+    static constexpr unsigned kRead = 7, kWrite = 5;
+    T lr, beta;
+    __device__ __forceinline__ void operator()(T (&v)[3], uint64_t) const {
+        const T nv = beta * v[2] + lr * v[1];
+        v[0] = v[0] - nv;
+        v[2] = nv;
+    }
+};
+
+template <typename T> struct AdagradF {  // adagrad.cl:42-46
+    static constexpr unsigned kRead = 7, kWrite = 5;
+    T lr;
+    __device__ __forceinline__ void operator()(T (&v)[3], uint64_t) const {
+        const T g = v[1];
+        const T h = v[2] + g * g;
+        v[0] = v[0] - lr * g / (sqrt(h) + (T)FLT_EPSILON);
+        v[2] = h;
+    }
+};
+
+template <typename T> struct RmspropF {  // rmsprop.cl:51-55
+    static constexpr unsigned kRead = 7, kWrite = 5;
+    T lr, gamma;
+    __device__ __forceinline__ void operator()(T (&v)[3], uint64_t) const {
+        const T g = v[1];
+        const T h = gamma * v[2] + ((T)1 - gamma) * g * g;
+        v[0] = v[0] - lr * g / (sqrt(h) + (T)FLT_EPSILON);
+        v[2] = h;
+    }
+};
+
+template <typename T> struct AdamF {  // textbook Adam (Kingma & Ba alg. 1); v = {x, g, m, v}
+    static constexpr unsigned kRead = 15, kWrite = 1 | 4 | 8;
+    T lr, b1, b2, eps, c1, c2;  // c1 = 1/(1-b1^t), c2 = 1/(1-b2^t)
+    __device__ __forceinline__ void operator()(T (&v)[4], uint64_t) const {
+        const T g = v[1];
+        const T m = b1 * v[2] + ((T)1 - b1) * g;
+        const T s = b2 * v[3] + ((T)1 - b2) * g * g;
+        v[0] = v[0] - lr * (m * c1) / (sqrt(s * c2) + eps);
+        v[2] = m;
+        v[3] = s;
+    }
+};
+
+// uniform.cl:32-54 (little-endian branch; `seed2 << 32` is always 0; `*` binds tighter than `^`)
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+__device__ __forceinline__ uint64_t wk_xxhash64(uint64_t index, uint64_t seed) {
+    const uint64_t key = (0x7C01812CF721AD1CULL ^ 0xDED46DE9839097DBULL) - seed;
+    const uint64_t combined = ((index & 0xFFFFFFFFULL) << 32) + (index >> 32);
+    const uint64_t x0 = combined ^ key;
+    const uint64_t x1 = x0 ^ rotl64(x0, 49) ^ (rotl64(x0, 24) * 0x9FB21C651E98DF25ULL);
+    const uint64_t x2 = x1 ^ (((x1 >> 35) + 8) * 0x9FB21C651E98DF25ULL);
+    return x2 ^ (x2 >> 28);
+}
+
+template <typename T, bool RANGE> struct UniformF {  // uniform.cl:56-185, idx = padded linear index
+    static constexpr unsigned kRead = 0, kWrite = 1;
+    uint64_t seed;
+    T min_value, range;
+    __device__ __forceinline__ void operator()(T (&v)[1], uint64_t idx) const {
+        const uint64_t h = wk_xxhash64(idx, seed);
+        if (RANGE) {
+            // cl_khr_fp64 branch: (double)h / ULONG_MAX; ULONG_MAX converts to 2^64
+            const double normalized = (double)h / 18446744073709551616.0;
+            v[0] = (T)((double)min_value + normalized * (double)range);
+        } else if (std::is_same<T, float>::value) {
+            v[0] = (T)((float)h / 18446744073709551616.0f);
+        } else if (std::is_same<T, double>::value) {
+            v[0] = (T)((double)h / 18446744073709551616.0);
+        } else {
+            v[0] = (T)h;  // & WK_UINT_MAX == truncation
+        }
+    }
+};
+
+// bias.cl:3-19: out[i] += bias[i % row_pitch].  Treated as a [n/rp, rp] matrix: a thread owns a 128-bit column
+// group, loads its bias values once and walks down the rows -- no per-element modulo.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias,
+                                                            uint64_t rp, uint64_t n_rows, uint64_t tail) {
+    const uint64_t col = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (col < rp) {
+        const T b = bias[col];
+        for (uint64_t r = blockIdx.y; r < n_rows; r += gridDim.y) out[r * rp + col] += b;
+        if (blockIdx.y == 0 && col < tail) out[n_rows * rp + col] += b;  // partial last row (n % rp)
+    }
+}
+
+template <typename T>
+__global__ void identity_kernel(T *__restrict__ buf, uint64_t size, uint64_t pitch_sum) {  // identity.cl:3-20
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < size) buf[i * pitch_sum] = (T)1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose2d_kernel(const T *__restrict__ src, uint64_t sp, T *__restrict__ dst,
+                                                          uint64_t dp, uint64_t rows, uint64_t cols) {
+    __shared__ T tile[32][33];
+    const uint64_t c0 = (uint64_t)blockIdx.x * 32, r0 = (uint64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const uint64_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[r * sp + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const uint64_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[c * dp + r] = tile[threadIdx.x][j];
+    }
+}
+
+// axpy.zig:66-91 isSubstracting
+template <typename T> static bool is_subtracting(const void *alpha) {
+    if (std::is_unsigned<T>::value) return false;
+    if (std::is_same<T, float>::value) return fabsf(*(const float *)alpha + 1.0f) < FLT_EPSILON;
+    if (std::is_same<T, double>::value) return fabs(*(const double *)alpha + 1.0) < DBL_EPSILON;
+    return *(const T *)alpha == (T)-1;
+}
+
+}  // namespace wk
+
+using namespace wk;
+
+WK_API int32_t wk_axpy(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *alpha,
+                       const void *x, uint64_t xrp, uint64_t xsp, void *y, uint64_t yrp, uint64_t ysp) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        Ptrs<2> p{{const_cast<void *>(x), y}};
+        Pitches<2> pit{{xrp, yrp}, {xsp, ysp}};
+        if (!alpha) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 0>{0});
+        if (is_subtracting<scalar_t>(alpha)) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 2>{0});
+        return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 1>{load_scalar<scalar_t>(alpha)});
+    });
+}
+
+WK_API int32_t wk_scal(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *alpha, void *x,
+                       uint64_t xrp, uint64_t xsp) {
+    WK_CHECK_QUEUE(q);
+    if (!alpha) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        Ptrs<1> p{{x}};
+        Pitches<1> pit{{xrp}, {xsp}};
+        return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, ScalF<scalar_t>{load_scalar<scalar_t>(alpha)});
+    });
+}
+
+WK_API int32_t wk_hadamard(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *x, uint64_t xrp,
+                           uint64_t xsp, const void *y, uint64_t yrp, uint64_t ysp) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        Ptrs<2> p{{x, const_cast<void *>(y)}};
+        Pitches<2> pit{{xrp, yrp}, {xsp, ysp}};
+        return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, HadamardF<scalar_t>{});
+    });
+}
+
+WK_API int32_t wk_fill(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *buf, uint64_t rp,
+                       uint64_t sp, const void *scalar) {
+    WK_CHECK_QUEUE(q);
+    if (!scalar) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        Ptrs<1> p{{buf}};
+        Pitches<1> pit{{rp}, {sp}};
+        return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, FillF<scalar_t>{*(const scalar_t *)scalar});
+    });
+}
+
+WK_API int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *buf, uint64_t rp,
+                          uint64_t sp, uint64_t seed, const void *minp, const void *maxp) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        Ptrs<1> p{{buf}};
+        Pitches<1> pit{{rp}, {sp}};
+        // the hash is taken over the PADDED linear index (uniform.cl:73): the dense fast path is only valid when
+        // padded index == dense index, which launch_map3d's density test guarantees.
+        if (minp || maxp) {
+            // uniform.zig:96-106: missing bound = type min / max (floats: -floatMax / floatMax); range = max - min in T
+            scalar_t mn = std::numeric_limits<scalar_t>::lowest(), mx = std::numeric_limits<scalar_t>::max();
+            if (minp) mn = *(const scalar_t *)minp;
+            if (maxp) mx = *(const scalar_t *)maxp;
+            const scalar_t range = (scalar_t)(mx - mn);
+            return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, true>{seed, mn, range});
+        }
+        return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, false>{seed, 0, 0});
+    });
+}
+
+WK_API int32_t wk_unary(wk_queue *q, int32_t dtype, int32_t op, void *x, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<1> p{{x}};
+        switch (op) {
+            case WK_OP_SIN: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_SIN>{});
+            case WK_OP_COS: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_COS>{});
+            case WK_OP_TAN: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_TAN>{});
+            case WK_OP_SINH: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_SINH>{});
+            case WK_OP_COSH: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_COSH>{});
+            case WK_OP_TANH: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_TANH>{});
+            case WK_OP_SIGMOID: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_SIGMOID>{});
+            default: set_error("unknown unary op %d", op); return WK_ERR_INVALID_VALUE;
+        }
+    });
+}
+
+WK_API int32_t wk_sigmoid_dev(wk_queue *q, int32_t dtype, const void *output, void *derivative, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<2> p{{const_cast<void *>(output), derivative}};
+        return launch_map<scalar_t, 2>(q, p, n, ActDevF<scalar_t, WK_ACT_SIGMOID>{});
+    });
+}
+
+WK_API int32_t wk_tanh_dev(wk_queue *q, int32_t dtype, const void *output, void *derivative, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<2> p{{const_cast<void *>(output), derivative}};
+        return launch_map<scalar_t, 2>(q, p, n, ActDevF<scalar_t, WK_ACT_TANH>{});
+    });
+}
+
+WK_API int32_t wk_act_backward(wk_queue *q, int32_t dtype, int32_t act, const void *output, void *derivative, void *sens,
+                               uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        // pointer slot 1 must be non-null for the launcher; alias it to `sens` when the derivative is not stored
+        Ptrs<3> p{{const_cast<void *>(output), derivative ? derivative : sens, sens}};
+        if (act == WK_ACT_SIGMOID) {
+            if (derivative) return launch_map<scalar_t, 3>(q, p, n, ActBackwardF<scalar_t, WK_ACT_SIGMOID, true>{});
+            return launch_map<scalar_t, 3>(q, p, n, ActBackwardF<scalar_t, WK_ACT_SIGMOID, false>{});
+        }
+        if (act == WK_ACT_TANH) {
+            if (derivative) return launch_map<scalar_t, 3>(q, p, n, ActBackwardF<scalar_t, WK_ACT_TANH, true>{});
+            return launch_map<scalar_t, 3>(q, p, n, ActBackwardF<scalar_t, WK_ACT_TANH, false>{});
+        }
+        set_error("unknown activation %d", act);
+        return WK_ERR_INVALID_VALUE;
+    });
+}
+
+WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void *bias, uint64_t row_pitch, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    if (!output || !bias) return WK_ERR_INVALID_BUFFER;
+    if (row_pitch == 0) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        const uint64_t n_rows = n / row_pitch, tail = n % row_pitch;
+        uint64_t gx = (row_pitch + kThreads - 1) / kThreads;
+        uint64_t gy = n_rows == 0 ? 1 : n_rows;
+        const uint64_t want = ((uint64_t)q->sm_count * kCtasPerSm + gx - 1) / gx;
+        if (gy > want) gy = want;
+        if (gy > 65535) gy = 65535;
+        bias_add_kernel<scalar_t><<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, q->stream>>>(
+            (scalar_t *)output, (const scalar_t *)bias, row_pitch, n_rows, tail);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}
+
+WK_API int32_t wk_mse(wk_queue *q, int32_t dtype, const void *output, const void *expected, void *err, void *dev, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<4> p{{const_cast<void *>(output), const_cast<void *>(expected), err, dev ? dev : err}};
+        if (dev) return launch_map<scalar_t, 4>(q, p, n, MseF<scalar_t, true>{});
+        return launch_map<scalar_t, 4>(q, p, n, MseF<scalar_t, false>{});
+    });
+}
+
+WK_API int32_t wk_gdm(wk_queue *q, int32_t dtype, void *x, const void *g, void *v, const void *lr, const void *beta, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    if (!lr || !beta) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<3> p{{x, const_cast<void *>(g), v}};
+        return launch_map<scalar_t, 3>(q, p, n, GdmF<scalar_t>{*(const scalar_t *)lr, *(const scalar_t *)beta});
+    });
+}
+
+WK_API int32_t wk_adagrad(wk_queue *q, int32_t dtype, void *x, const void *g, void *h, const void *lr, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    if (!lr) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<3> p{{x, const_cast<void *>(g), h}};
+        return launch_map<scalar_t, 3>(q, p, n, AdagradF<scalar_t>{*(const scalar_t *)lr});
+    });
+}
+
+WK_API int32_t wk_rmsprop(wk_queue *q, int32_t dtype, void *x, const void *g, void *h, const void *lr, const void *gamma,
+                          uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    if (!lr || !gamma) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<3> p{{x, const_cast<void *>(g), h}};
+        return launch_map<scalar_t, 3>(q, p, n, RmspropF<scalar_t>{*(const scalar_t *)lr, *(const scalar_t *)gamma});
+    });
+}
+
+WK_API int32_t wk_adam(wk_queue *q, int32_t dtype, void *x, const void *g, void *m, void *v, const void *lr, const void *b1,
+                       const void *b2, const void *eps, uint64_t t, uint64_t n) {
+    WK_CHECK_QUEUE(q);
+    if (!lr || !b1 || !b2 || !eps || t == 0) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        Ptrs<4> p{{x, const_cast<void *>(g), m, v}};
+        const double B1 = (double)*(const scalar_t *)b1, B2 = (double)*(const scalar_t *)b2;
+        AdamF<scalar_t> f{*(const scalar_t *)lr, *(const scalar_t *)b1, *(const scalar_t *)b2, *(const scalar_t *)eps,
+                          (scalar_t)(1.0 / (1.0 - pow(B1, (double)t))), (scalar_t)(1.0 / (1.0 - pow(B2, (double)t)))};
+        return launch_map<scalar_t, 4>(q, p, n, f);
+    });
+}
+
+WK_API int32_t wk_identity(wk_queue *q, int32_t dtype, void *buf, uint64_t n_total, uint64_t size, uint64_t pitch_sum) {
+    WK_CHECK_QUEUE(q);
+    if (!buf) return WK_ERR_INVALID_BUFFER;
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        WK_CUDA(cudaMemsetAsync(buf, 0, n_total * sizeof(scalar_t), q->stream));  // fill.zeroes, identity.zig:28
+        identity_kernel<scalar_t><<<(unsigned)((size + 255) / 256), 256, 0, q->stream>>>((scalar_t *)buf, size, pitch_sum);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}
+
+WK_API int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_t cols, const void *src, uint64_t sp,
+                              void *dst, uint64_t dp) {
+    WK_CHECK_QUEUE(q);
+    if (!src || !dst) return WK_ERR_INVALID_BUFFER;
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+        if (grid.y > 65535) {
+            set_error("transpose2d: too many rows");
+            return WK_ERR_INVALID_VALUE;
+        }
+        transpose2d_kernel<scalar_t><<<grid, dim3(32, 8), 0, q->stream>>>((const scalar_t *)src, sp, (scalar_t *)dst, dp,
+                                                                        rows, cols);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}

@@ -1,0 +1,225 @@
+// reduce.cu -- reductions of the hot path: math.sum (src/math/basic.zig:131-203 + kernels/sum.cl), the
+// column sum of Linear.getBiasSensitivity (src/nn/layer/linear.zig:534-577 + bias_step.cl) and the BLAS-style
+// reduction dot named by the north star.  Two-stage, atomic-free and deterministic: stage 1 is a grid-strided
+// 128-bit streaming read with warp-shuffle + shared-memory block reduction into per-block partials, stage 2 a
+// single block folding the partials; the scalar then travels through pinned memory (the reference blocks on a
+// mapped read at the same point, basic.zig:154-171).
+#include "common.cuh"
+
+namespace wk {
+
+constexpr int kRThreads = 256;
+
+template <typename A> __device__ __forceinline__ A shfl_xor(A v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ uint64_t shfl_xor<uint64_t>(uint64_t v, int m) {
+    return (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
+}
+
+template <typename A> __device__ __forceinline__ A block_reduce_sum(A v) {
+    __shared__ A warp_part[kRThreads / 32];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = v + shfl_xor<A>(v, m);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    A r = (A)0;
+    if (warp == 0) {
+        r = lane < kRThreads / 32 ? warp_part[lane] : (A)0;
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) r = r + shfl_xor<A>(r, m);
+    }
+    __syncthreads();
+    return r;  // valid in thread 0
+}
+
+// Runs: n_runs contiguous runs of run_len elements; run r starts at (r / rows) * sp + (r % rows) * rp.
+// NIN = 1: sum of x; NIN = 2: sum of x*y (y has its own pitches).
+template <typename T, int NIN, bool VECTOR>
+__global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restrict__ x, const T *__restrict__ y,
+                                                                uint64_t run_len, uint64_t n_runs, uint64_t rows,
+                                                                uint64_t xrp, uint64_t xsp, uint64_t yrp, uint64_t ysp,
+                                                                typename Acc<T>::type *__restrict__ partial) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    union Pack { uint4 u; T e[VEC]; };
+    A acc[4] = {(A)0, (A)0, (A)0, (A)0};
+    for (uint64_t r = blockIdx.y; r < n_runs; r += gridDim.y) {
+        const uint64_t d = r / rows, j = r - d * rows;
+        const T *xr = x + d * xsp + j * xrp;
+        const T *yr = NIN == 2 ? y + d * ysp + j * yrp : nullptr;
+        if (VECTOR) {
+            const uint64_t nv = run_len / VEC;
+            const uint4 *xv = reinterpret_cast<const uint4 *>(xr);
+            const uint4 *yv = reinterpret_cast<const uint4 *>(yr);
+            const uint64_t stride = (uint64_t)gridDim.x * kRThreads;
+            uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x;
+            // 4 independent 128-bit loads in flight per operand
+            for (; i + 3 * stride < nv; i += 4 * stride) {
+                Pack px[4], py[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    px[u].u = __ldg(xv + i + u * stride);
+                    if (NIN == 2) py[u].u = __ldg(yv + i + u * stride);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int e = 0; e < VEC; e++)
+                        acc[u] = acc[u] + (NIN == 2 ? to_acc<T>(px[u].e[e]) * to_acc<T>(py[u].e[e]) : to_acc<T>(px[u].e[e]));
+            }
+            for (; i < nv; i += stride) {
+                Pack px, py;
+                px.u = __ldg(xv + i);
+                if (NIN == 2) py.u = __ldg(yv + i);
+#pragma unroll
+                for (int e = 0; e < VEC; e++)
+                    acc[0] = acc[0] + (NIN == 2 ? to_acc<T>(px.e[e]) * to_acc<T>(py.e[e]) : to_acc<T>(px.e[e]));
+            }
+        } else {
+            for (uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x; i < run_len; i += (uint64_t)gridDim.x * kRThreads)
+                acc[0] = acc[0] + (NIN == 2 ? to_acc<T>(xr[i]) * to_acc<T>(yr[i]) : to_acc<T>(xr[i]));
+        }
+    }
+    A v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    v = block_reduce_sum<A>(v);
+    if (threadIdx.x == 0) partial[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRThreads) reduce_final_kernel(const typename Acc<T>::type *__restrict__ partial,
+                                                                 uint64_t n, T *__restrict__ out) {
+    using A = typename Acc<T>::type;
+    A v = (A)0;
+    for (uint64_t i = threadIdx.x; i < n; i += kRThreads) v = v + partial[i];
+    v = block_reduce_sum<A>(v);
+    if (threadIdx.x == 0) *out = from_acc<T>(v);
+}
+
+template <typename T, int NIN>
+static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, uint64_t rows, uint64_t run_len, uint64_t xrp,
+                           uint64_t xsp, uint64_t yrp, uint64_t ysp, void *host_out) {
+    using A = typename Acc<T>::type;
+    if (!x || (NIN == 2 && !y) || !host_out) return WK_ERR_INVALID_BUFFER;
+    if (depth == 0 || rows == 0 || run_len == 0) return WK_ERR_INVALID_VALUE;
+    // collapse contiguous runs
+    if (rows > 1 && xrp == run_len && (NIN == 1 || yrp == run_len)) { run_len *= rows; rows = 1; }
+    if (rows == 1 && depth > 1 && xsp == run_len && (NIN == 1 || ysp == run_len)) { run_len *= depth; depth = 1; }
+    const uint64_t n_runs = depth * rows;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    bool vec = aligned16(x) && run_len % VEC == 0 && (n_runs == 1 || (xrp % VEC == 0 && xsp % VEC == 0));
+    if (NIN == 2) vec = vec && aligned16(y) && (n_runs == 1 || (yrp % VEC == 0 && ysp % VEC == 0));
+    const uint64_t per_block = (uint64_t)kRThreads * (vec ? VEC * 4 : 4);
+    uint64_t gx = (run_len + per_block - 1) / per_block;
+    const uint64_t cap = (uint64_t)q->sm_count * 8;
+    if (gx > cap) gx = cap;
+    uint64_t gy = n_runs;
+    const uint64_t cap_y = (cap + gx - 1) / gx;
+    if (gy > cap_y) gy = cap_y;
+    if (gy > 65535) gy = 65535;
+    const uint64_t n_part = gx * gy;
+    int32_t rc = ensure_scratch(q, n_part * sizeof(A) + 64);
+    if (rc != WK_OK) return rc;
+    A *partial = reinterpret_cast<A *>((char *)q->scratch + 64);
+    T *result = reinterpret_cast<T *>(q->scratch);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec)
+        reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
+    else
+        reduce_runs_kernel<T, NIN, false><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
+    WK_CHECK_LAUNCH();
+    reduce_final_kernel<T><<<1, kRThreads, 0, q->stream>>>(partial, n_part, result);
+    WK_CHECK_LAUNCH();
+    WK_CUDA(cudaMemcpyAsync(q->pinned, result, sizeof(T), cudaMemcpyDeviceToHost, q->stream));
+    WK_CUDA(cudaStreamSynchronize(q->stream));
+    *(T *)host_out = *(const T *)q->pinned;
+    return WK_OK;
+}
+
+// bias_step.cl:24-37.  Stage 1: thread (c, chunk) sums rows [chunk*rows_per, ...) of column c in ascending row
+// order (coalesced across c); stage 2 folds the chunks in ascending order.  With one chunk the summation order
+// is exactly the reference's.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, uint64_t rp, uint64_t rows, uint64_t n_cols,
+                                                     uint64_t rows_per, T *__restrict__ out, uint64_t out_pitch) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cols) return;
+    const uint64_t r0 = (uint64_t)blockIdx.y * rows_per;
+    uint64_t r1 = r0 + rows_per;
+    if (r1 > rows) r1 = rows;
+    T acc = (T)0;
+    const T *p = s + r0 * rp + c;
+    uint64_t r = r0;
+    for (; r + 4 <= r1; r += 4, p += 4 * rp) {  // 4 loads in flight, summed in order
+        const T a0 = p[0], a1 = p[rp], a2 = p[2 * rp], a3 = p[3 * rp];
+        acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; r < r1; r++, p += rp) acc += *p;
+    out[(uint64_t)blockIdx.y * out_pitch + c] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_stage2(const T *__restrict__ part, uint64_t n_chunks, uint64_t pitch,
+                                                     uint64_t n_cols, T *__restrict__ out) {
+    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cols) return;
+    T acc = (T)0;
+    for (uint64_t k = 0; k < n_chunks; k++) acc += part[k * pitch + c];
+    out[c] = acc;
+}
+
+}  // namespace wk
+
+using namespace wk;
+
+WK_API int32_t wk_sum(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t row_pitch, uint64_t slice_pitch,
+                      const void *x, void *host_out) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        return reduce_runs<scalar_t, 1>(q, (const scalar_t *)x, nullptr, depth, rows, row_pitch, row_pitch, slice_pitch, 0, 0,
+                                        host_out);
+    });
+}
+
+WK_API int32_t wk_dot_reduce(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *x,
+                             uint64_t xrp, uint64_t xsp, const void *y, uint64_t yrp, uint64_t ysp, void *host_out) {
+    WK_CHECK_QUEUE(q);
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        return reduce_runs<scalar_t, 2>(q, (const scalar_t *)x, (const scalar_t *)y, depth, rows, cols, xrp, xsp, yrp, ysp,
+                                        host_out);
+    });
+}
+
+WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *bias_grad, uint64_t row_pitch, uint64_t rows,
+                            uint64_t n_cols) {
+    WK_CHECK_QUEUE(q);
+    if (!sens || !bias_grad) return WK_ERR_INVALID_BUFFER;
+    if (n_cols == 0) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        const uint64_t gx = (n_cols + 255) / 256;
+        // enough chunks to fill the machine, but never split short columns (keeps the reference's order)
+        uint64_t chunks = 1;
+        if (rows > 256) {
+            chunks = ((uint64_t)q->sm_count * 4 + gx - 1) / gx;
+            const uint64_t max_chunks = (rows + 63) / 64;
+            if (chunks > max_chunks) chunks = max_chunks;
+            if (chunks > 65535) chunks = 65535;
+            if (chunks < 1) chunks = 1;
+        }
+        const uint64_t rows_per = (rows + chunks - 1) / chunks;
+        if (chunks == 1) {
+            colsum_stage1<scalar_t><<<dim3((unsigned)gx, 1), 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols,
+                                                                              rows_per, (scalar_t *)bias_grad, 0);
+            WK_CHECK_LAUNCH();
+            return WK_OK;
+        }
+        int32_t rc = ensure_scratch(q, chunks * n_cols * sizeof(scalar_t));
+        if (rc != WK_OK) return rc;
+        colsum_stage1<scalar_t><<<dim3((unsigned)gx, (unsigned)chunks), 256, 0, q->stream>>>(
+            (const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, (scalar_t *)q->scratch, n_cols);
+        WK_CHECK_LAUNCH();
+        colsum_stage2<scalar_t><<<(unsigned)gx, 256, 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
+                                                                    (scalar_t *)bias_grad);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}
