@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/tc_check.py f32 > gpurun_out/tc_check_f32.log 2>&1; echo "tc_check exit $?" >> gpurun_out/tc_check_f32.log
+tail -45 gpurun_out/tc_check_f32.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log

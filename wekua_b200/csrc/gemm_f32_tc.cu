@@ -1,8 +1,348 @@
-// placeholder until the tcgen05 kernel lands
+// gemm_f32_tc.cu -- f32 blas.gemm on the 5th-generation tensor cores: 3xTF32 split with fp32 accumulation in TMEM.
+//
+//   C[M,N] = alpha * op(A) * op(B) + beta * C        (src/blas/gemm.zig:834-874, all four transpose pairs)
+//
+// Every fp32 operand x is split on the fly into hi = tf32(x) and lo = tf32(x - hi); the product is accumulated as
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the lo*lo term, <= 2^-22 relative, is dropped), which keeps the result at fp32
+// level while all multiplies run on tcgen05.mma.kind::tf32.
+//
+// Structure (one persistent CTA per SM, static tile schedule, 128 x 256 output tile, k-block = 32 = one 128-byte
+// swizzle row):
+//   warp 0      TMA producer   : cp.async.bulk.tensor (128B swizzle, zero fill out of bounds) -> raw fp32 stage
+//   warps 2-9   converters     : raw -> hi (in place) and lo (second buffer), same swizzled layout, 128-bit smem ops
+//   warp 1      MMA issuer     : one elected thread issues 12 tcgen05.mma per k-block (4 k-steps x 3 split terms) into
+//                                a 128x256 fp32 TMEM accumulator; tcgen05.commit frees the smem stage / publishes the tile
+//   warps 10-13 epilogue       : tcgen05.ld -> alpha/beta/bias/activation -> global (and peer GPUs for the fused
+//                                all-gather); two TMEM accumulators (2 x 256 columns) let it overlap the next tile
+// The transpose variants only change the TMA boxes and the UMMA descriptors (K-major vs MN-major operands); the
+// converters are layout-agnostic because hi/lo keep the byte layout TMA produced.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace wk {
-int32_t gemm_f32_tc(wk_queue *, int32_t, int32_t, uint64_t, uint64_t, uint64_t, const float *, const float *, uint64_t,
-                    const float *, uint64_t, const float *, float *, uint64_t, const float *, int32_t, const GemmPeers *) {
-    return -1;
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;              // 16 KiB
+constexpr int B_BYTES = BN * BK * 4;              // 32 KiB
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;      // hi tiles (TMA lands here), 48 KiB
+constexpr int STAGE_BYTES = 2 * RAW_BYTES;        // + lo tiles
+constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
+constexpr int THREADS = (2 + CONV_WARPS + EPI_WARPS) * 32;  // 448
+constexpr int TMEM_COLS = 512;                    // two 128x256 fp32 accumulators
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Params {
+    float *C;
+    uint64_t M, N, K, ldc;
+    float alpha, beta;
+    int has_alpha, has_beta;
+    const float *bias;
+    int act;
+    int op_a, op_b;
+    uint32_t tiles_m, tiles_n;
+    int n_peers, self;
+    float *peers[16];
+};
+
+struct Barriers {
+    uint64_t raw_full[STAGES];    // TMA -> converters
+    uint64_t conv_done[STAGES];   // converters -> MMA
+    uint64_t stage_free[STAGES];  // MMA (commit) -> TMA
+    uint64_t acc_full[2];         // MMA (commit) -> epilogue
+    uint64_t acc_empty[2];        // epilogue -> MMA
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &tm, uint32_t &tn) {
+    // groups of 8 row-tiles sweep the columns together so concurrently resident tiles share A and B panels in L2
+    constexpr uint32_t GM = 8;
+    const uint32_t per_group = GM * tiles_n;
+    const uint32_t group = t / per_group, in_group = t - group * per_group;
+    const uint32_t first_m = group * GM;
+    const uint32_t gsize = min(GM, tiles_m - first_m);
+    tm = first_m + in_group % gsize;
+    tn = in_group / gsize;
 }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == WK_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (act == WK_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&bars->raw_full[s], 1);
+            mbar_init(&bars->conv_done[s], CONV_WARPS);
+            mbar_init(&bars->stage_free[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&bars->acc_full[a], 1);
+            mbar_init(&bars->acc_empty[a], EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                uint32_t tm, tn;
+                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+                const int32_t m0 = (int32_t)(tm * BM), n0 = (int32_t)(tn * BN);
+                for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&bars->stage_free[s], ph ^ 1);
+                    uint8_t *a_dst = smem + s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
+                    mbar_arrive_expect_tx(&bars->raw_full[s], RAW_BYTES);
+                    const int32_t k0 = (int32_t)(kb * BK);
+                    if (p.op_a == 0) {  // A[M][K]: one 32(k) x 128(m) box, K-major
+                        tma_load_2d(a_dst, &tmA, k0, m0, &bars->raw_full[s]);
+                    } else {            // A[K][M]: four 32(m) x 32(k) boxes, MN-major
+                        for (int j = 0; j < BM / 32; j++) tma_load_2d(a_dst + j * 4096, &tmA, m0 + 32 * j, k0, &bars->raw_full[s]);
+                    }
+                    if (p.op_b == 1) {  // B[N][K]: one 32(k) x 256(n) box, K-major
+                        tma_load_2d(b_dst, &tmB, k0, n0, &bars->raw_full[s]);
+                    } else {            // B[K][N]: eight 32(n) x 32(k) boxes, MN-major
+                        for (int j = 0; j < BN / 32; j++) tma_load_2d(b_dst + j * 4096, &tmB, n0 + 32 * j, k0, &bars->raw_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(BM, BN, p.op_a == 1, p.op_b == 0);
+        // K-major tile (SW128): 128-byte rows of 32 k, 8-row groups 1024 B apart (SBO).
+        // MN-major tile (SW128 with 32-byte atoms): 128-byte rows of 32 mn, one row per k, atoms of 4 k-rows = 512 B
+        // (SBO), 32-wide MN chunks 4096 B apart (LBO).
+        const uint64_t a_base = p.op_a == 0 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
+        const uint64_t b_base = p.op_b == 1 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
+        const uint32_t a_kstep = p.op_a == 0 ? 32 : 1024;  // bytes per k-step of 8
+        const uint32_t b_kstep = p.op_b == 1 ? 32 : 1024;
+        uint32_t it = 0, tile_i = 0;
+        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_i++) {
+            const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
+            mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&bars->conv_done[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
+                    const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = b_hi + RAW_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; k++) {
+                        const uint64_t dah = umma_desc(a_base, a_hi + k * a_kstep), dal = umma_desc(a_base, a_lo + k * a_kstep);
+                        const uint64_t dbh = umma_desc(b_base, b_hi + k * b_kstep), dbl = umma_desc(b_base, b_lo + k * b_kstep);
+                        mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+                        mma_tf32_ss(d_tmem, dah, dbl, idesc, 1);
+                        mma_tf32_ss(d_tmem, dah, dbh, idesc, 1);
+                    }
+                    mma_commit(&bars->stage_free[s]);                       // smem stage reusable once these MMAs retire
+                    if (kb == num_kb - 1) mma_commit(&bars->acc_full[acc]);  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 2 + CONV_WARPS) {
+        // ================================================================= converters: raw -> (hi, lo)
+        const int ct = threadIdx.x - 64;  // 0..255
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&bars->raw_full[s], ph);
+                float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + RAW_BYTES);
+#pragma unroll
+                for (int j = 0; j < RAW_BYTES / 16 / (CONV_WARPS * 32); j++) {
+                    const int i = ct + j * (CONV_WARPS * 32);
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    float hs[4], ls[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        uint32_t hb, lb;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs[e]));
+                        const float hf = __uint_as_float(hb);
+                        // inf - inf would poison the product: a non-finite hi carries the value alone
+                        const float rem = (hb & 0x7f800000u) == 0x7f800000u ? 0.0f : xs[e] - hf;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+                        hs[e] = hf;
+                        ls[e] = __uint_as_float(lb);
+                    }
+                    h = make_float4(hs[0], hs[1], hs[2], hs[3]);
+                    l = make_float4(ls[0], ls[1], ls[2], ls[3]);
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->conv_done[s]);
+            }
+        }
+    } else {
+        // ================================================================= epilogue
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t tile_i = 0;
+        const bool vec_ok = (p.ldc % 4 == 0);
+        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_i++) {
+            uint32_t tm, tn;
+            tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+            const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
+            mbar_wait(&bars->acc_full[acc], acc_ph);
+            tc_fence_after();
+            const uint64_t row = (uint64_t)tm * BM + q * 32 + lane;
+            const uint64_t col0 = (uint64_t)tn * BN;
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                }
+                const uint64_t col = col0 + (uint64_t)c * 32;
+                if (row < p.M && col < p.N) {
+                    float *crow = p.C + row * p.ldc + col;
+                    const bool full = vec_ok && (col + 32 <= p.N);
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            v[e] = __uint_as_float(r[g * 4 + e]);
+                            if (p.has_alpha) v[e] *= p.alpha;
+                        }
+                        if (full) {
+                            if (p.has_beta) {
+                                const float4 o = *reinterpret_cast<const float4 *>(crow + g * 4);
+                                v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
+                            }
+                            if (p.bias) {
+                                const float4 bv = *reinterpret_cast<const float4 *>(p.bias + col + g * 4);
+                                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+                            }
+                            if (p.act) {
+#pragma unroll
+                                for (int e = 0; e < 4; e++) v[e] = apply_act(v[e], p.act);
+                            }
+                            const float4 out = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4 *>(crow + g * 4) = out;
+                            for (int pi = 0; pi < p.n_peers; pi++)
+                                if (pi != p.self)
+                                    *reinterpret_cast<float4 *>(p.peers[pi] + row * p.ldc + col + g * 4) = out;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const uint64_t cc = col + g * 4 + e;
+                                if (cc < p.N) {
+                                    float o = v[e];
+                                    if (p.has_beta) o += p.beta * crow[g * 4 + e];
+                                    if (p.bias) o += p.bias[cc];
+                                    o = apply_act(o, p.act);
+                                    crow[g * 4 + e] = o;
+                                    for (int pi = 0; pi < p.n_peers; pi++)
+                                        if (pi != p.self) p.peers[pi][row * p.ldc + cc] = o;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+
+int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K, const float *alpha,
+                    const float *A, uint64_t lda, const float *B, uint64_t ldb, const float *beta, float *C, uint64_t ldc,
+                    const float *bias, int32_t act, const GemmPeers *peers) {
+    using namespace tc;
+    // TMA needs 16-byte aligned bases and pitches; the epilogue wants 16-byte aligned C rows
+    if (!aligned16(A) || !aligned16(B) || !aligned16(C) || (lda % 4) || (ldb % 4) || (ldc % 4)) return -1;
+    if (bias && !aligned16(bias)) return -1;
+    if (q->prop.major != 10) return -1;
+    if (M > 0x7fffffffULL || N > 0x7fffffffULL || K > 0x7fffffffULL) return -1;
+    if (peers)
+        for (int i = 0; i < peers->n; i++)
+            if (!aligned16(peers->ptrs[i])) return -1;
+
+    CUtensorMap tmA, tmB;
+    bool ok;
+    if (op_a == 0) ok = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, A, K, M, lda * 4, BK, BM);
+    else ok = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, A, M, K, lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (op_b == 1) ok = ok && make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, B, K, N, ldb * 4, BK, BN);
+    else ok = ok && make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, B, N, K, ldb * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (!ok) {
+        set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed");
+        return WK_ERR_CUDA;
+    }
+
+    Params p{};
+    p.C = C;
+    p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+    p.has_alpha = (alpha != nullptr || beta != nullptr);
+    p.has_beta = (beta != nullptr);
+    p.alpha = alpha ? *alpha : 1.0f;
+    p.beta = beta ? *beta : 0.0f;
+    p.bias = bias;
+    p.act = act;
+    p.op_a = op_a; p.op_b = op_b;
+    p.tiles_m = (uint32_t)((M + BM - 1) / BM);
+    p.tiles_n = (uint32_t)((N + BN - 1) / BN);
+    p.n_peers = 0;
+    p.self = 0;
+    if (peers && peers->n > 1) {
+        p.n_peers = peers->n;
+        p.self = peers->self;
+        for (int i = 0; i < peers->n; i++) p.peers[i] = (float *)peers->ptrs[i];
+    }
+
+    static bool attr_set[64] = {false};
+    if (!attr_set[q->device & 63]) {
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[q->device & 63] = true;
+    }
+    const uint64_t num_tiles = (uint64_t)p.tiles_m * p.tiles_n;
+    const unsigned grid = (unsigned)(num_tiles < (uint64_t)q->sm_count ? num_tiles : (uint64_t)q->sm_count);
+    gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, q->stream>>>(tmA, tmB, p);
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
+
 }  // namespace wk

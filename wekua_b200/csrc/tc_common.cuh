@@ -1,0 +1,247 @@
+// tc_common.cuh -- sm_100a building blocks for the tensor-core GEMMs: mbarrier, TMA (cp.async.bulk.tensor),
+// tcgen05 (TMEM alloc / mma / commit / ld), UMMA shared-memory and instruction descriptors, host-side tensor maps.
+// Inline PTX only; descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction
+// descriptor" tables.
+#pragma once
+
+#include <cuda.h>  // CUtensorMap (types only; the driver entry point is fetched at run time, libcuda is not linked)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wk {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------- misc
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta_rank) {
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\t"
+        "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta_rank)
+        : "memory");
+}
+
+// Bounded wait: a protocol bug must trap (kills the context) instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > 4096) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 6000000000LL) {  // ~3 s
+                printf("wekua_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                       addr, parity);
+                __trap();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+// 2-D tile load: c0 = coordinate along the contiguous (inner) dimension, c1 = outer; completes tx bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// same, but the data lands at the same smem offset and signals the same barrier offset in CTA `cta` of the pair
+__device__ __forceinline__ void tma_load_2d_cta_group2(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1,
+                                                       uint64_t *bar_leader_mapped_addr_holder, uint32_t bar_addr_cluster) {
+    (void)bar_leader_mapped_addr_holder;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(m), "r"(c0), "r"(c1), "r"(bar_addr_cluster)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_holder, uint32_t ncols) {  // one full warp; ncols pow2 >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t *smem_holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand from TMEM
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_commit_2cta_multicast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread t = lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};" ::"r"(r[0]),
+        "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+        "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (64 bit): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1,
+// [61,64) layout type.  Tiles are 1024-byte aligned so base_offset = 0.
+//   UMMA_SW128      (2): 128-byte swizzle, 16-byte atoms  -- K-major operands (TMA CU_TENSOR_MAP_SWIZZLE_128B)
+//   UMMA_SW128_32B  (1): 128-byte swizzle, 32-byte atoms  -- the only layout tf32 accepts for MN-major operands
+//                        (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 MN-contiguous floats, 4 k-rows per atom
+constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_32B = 1;
+__host__ __device__ constexpr uint64_t umma_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = UMMA_SW128) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint64_t base, uint32_t smem_addr) { return base | (uint64_t)((smem_addr >> 4) & 0x3FFF); }
+
+// Instruction descriptor (32 bit) for kind::tf32 with fp32 accumulate:
+// [4,6) D fmt = 1 (f32), [7,10) A fmt = 2 (tf32), [10,13) B fmt = 2, [15] A major (0 K, 1 MN), [16] B major,
+// [17,23) N >> 3, [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [outer][inner] with row pitch `pitch_bytes`; box = box_inner x box_outer elements, 128B swizzle,
+// out-of-bounds elements read as zero.
+inline bool make_tmap_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t outer,
+                         uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+}  // namespace wk
