@@ -61,8 +61,11 @@ def test_xor_training_matches_oracle(oracle, dtype, fused):
     oracle.mse(ref.forward(), ref.t, ref.err, None)
     ref_err = float(oracle.mean(ref.err))
     assert math.isfinite(float(err)) and abs(float(err) - ref_err) <= 1e-4 * max(1.0, abs(ref_err))
-    logical = float(np.mean((out - TARGETS.reshape(-1)) ** 2))
-    assert abs(float(err) - (logical + 0.25)) < 1e-3  # 4 padded elements of 0.25 each, divided by the 4 logical ones
+    # closed form of that value: for a [4,1] tensor math.sum adds the first 4 elements of the pitch-2 BUFFER
+    # (basic.zig:150-152,193-202), i.e. err[0], pad, err[1], pad with pad = (0 - sigmoid(0))^2 = 0.25, and mean divides
+    # by the 4 logical elements
+    e = (out.astype(np.float64) - TARGETS.reshape(-1)) ** 2
+    assert abs(float(err) - (e[0] + e[1] + 0.5) / 4) < 1e-4
     opt.deinit(pipe)
     cache.deinit(pipe)
     seq.deinit(pipe)

@@ -2,6 +2,8 @@
 plus scal / dot_reduce which the north star names but src/ lacks."""
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from . import capi
@@ -80,6 +82,38 @@ def gemm(pipeline: Pipeline, alpha, a: Tensor, op_a: int, b: Tensor, op_b: int, 
     be, pbe = _scalar(c.dtype, beta)
     capi.check(capi.lib().wk_gemm(pipeline.q, c.type_index, op_a, op_b, M, N, K, pal, a.ptr, a.row_pitch, b.ptr,
                                   b.row_pitch, pbe, c.ptr, c.row_pitch))
+    finish_c_padding(pipeline, c, beta)
+
+
+def _pad_regions(c: Tensor):
+    """(byte offset, rows, cols) of the padding of a 2-D tensor: the pad columns of every padded row, then the pad
+    row's logical columns (vector width 1: at most one pad column and one pad row, main.zig:168,185-187)"""
+    M, N = c.shape
+    es = c.dtype.itemsize
+    regions = []
+    if c.row_pitch > N:
+        regions.append((N * es, c.rows_padded, c.row_pitch - N))
+    if c.rows_padded > M:
+        regions.append((M * c.row_pitch * es, c.rows_padded - M, N))
+    return regions
+
+
+def finish_c_padding(pipeline: Pipeline, c: Tensor, beta, value=None) -> None:
+    """The reference's GEMM kernels run over the whole PADDED C (global size rows_padded/2 x row_pitch/2,
+    work_configuration.zig:166-186) and, on the packed path Linear and the benchmark use, the packed operands are
+    zero outside the logical shape (gemm_pack.cl:89-91): C's padding becomes beta*padding, or 0 when beta is null.
+    wk_gemm writes the logical M x N block only (C may be a row block of a larger matrix), so the host mirror
+    finishes the padding of whole tensors here -- at most two tiny launches, and none for even shapes."""
+    if not getattr(c, "_owns", True):
+        return  # a view over someone else's memory has no padding of its own
+    for off, rows, cols in _pad_regions(c):
+        ptr = C.c_void_p(c.buffer + off)
+        if beta is None or value is not None:
+            v, pv = _scalar(c.dtype, 0 if value is None else value)
+            capi.check(capi.lib().wk_fill(pipeline.q, c.type_index, 1, rows, cols, ptr, c.row_pitch, c.slice_pitch, pv))
+        else:
+            v, pv = _scalar(c.dtype, beta)
+            capi.check(capi.lib().wk_scal(pipeline.q, c.type_index, 1, rows, cols, pv, ptr, c.row_pitch, c.slice_pitch))
 
 
 def axpy(pipeline: Pipeline, x: Tensor, alpha, y: Tensor) -> None:

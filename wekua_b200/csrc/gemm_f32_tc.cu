@@ -6,32 +6,44 @@
 // a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the lo*lo term, <= 2^-22 relative, is dropped), which keeps the result at fp32
 // level while all multiplies run on tcgen05.mma.kind::tf32.
 //
-// Structure (one persistent CTA per SM, static tile schedule, 128 x 256 output tile, k-block = 32 = one 128-byte
-// swizzle row):
+// Structure (persistent, static tile schedule, k-block = 32 = one 128-byte swizzle row).  Template parameter CTAS:
+//   CTAS = 1  one CTA per SM, 128 x 256 output tile, tcgen05.mma.cta_group::1 (M = 128)
+//   CTAS = 2  CTA pairs (cluster of 2), 256 x 256 output tile, tcgen05.mma.cta_group::2 (M = 256): each CTA stages
+//             its own 128 rows of A and its own 128 columns of B, so the shared-memory traffic per flop -- the
+//             measured limiter of the CTAS = 1 kernel (profiles/ncu_gemm_f32_r01a.txt) -- drops by a third.
 //   warp 0      TMA producer   : cp.async.bulk.tensor (128B swizzle, zero fill out of bounds) -> raw fp32 stage
 //   warps 2-9   converters     : raw -> hi (in place) and lo (second buffer), same swizzled layout, 128-bit smem ops
-//   warp 1      MMA issuer     : one elected thread issues 12 tcgen05.mma per k-block (4 k-steps x 3 split terms) into
-//                                a 128x256 fp32 TMEM accumulator; tcgen05.commit frees the smem stage / publishes the tile
+//   warp 1      MMA issuer     : one elected thread (leader CTA) issues 12 tcgen05.mma per k-block (4 k-steps x 3 split
+//                                terms) into a fp32 TMEM accumulator; tcgen05.commit frees the smem stage / publishes the tile
 //   warps 10-13 epilogue       : tcgen05.ld -> alpha/beta/bias/activation -> global (and peer GPUs for the fused
 //                                all-gather); two TMEM accumulators (2 x 256 columns) let it overlap the next tile
 // The transpose variants only change the TMA boxes and the UMMA descriptors (K-major vs MN-major operands); the
 // converters are layout-agnostic because hi/lo keep the byte layout TMA produced.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace wk {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4;              // 16 KiB
-constexpr int B_BYTES = BN * BK * 4;              // 32 KiB
-constexpr int RAW_BYTES = A_BYTES + B_BYTES;      // hi tiles (TMA lands here), 48 KiB
-constexpr int STAGE_BYTES = 2 * RAW_BYTES;        // + lo tiles
+constexpr int BM = 128;   // rows of A / C per CTA
+constexpr int BN = 256;   // columns of the output tile (UMMA N)
+constexpr int BK = 32;    // one 128-byte swizzle row of fp32
 constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
 constexpr int THREADS = (2 + CONV_WARPS + EPI_WARPS) * 32;  // 448
-constexpr int TMEM_COLS = 512;                    // two 128x256 fp32 accumulators
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;                               // two 128x256 fp32 accumulators
+constexpr int MAX_STAGES = 3;
+
+template <int CTAS> struct Cfg {
+    static constexpr int BN_LOAD = BN / CTAS;          // B columns staged by each CTA
+    static constexpr int A_BYTES = BM * BK * 4;        // 16 KiB
+    static constexpr int B_BYTES = BN_LOAD * BK * 4;   // 32 / 16 KiB
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;  // hi tiles (TMA lands here)
+    static constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // + lo tiles
+    static constexpr int STAGES = CTAS == 1 ? 2 : 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct Params {
     float *C;
@@ -41,17 +53,18 @@ struct Params {
     const float *bias;
     int act;
     int op_a, op_b;
+    int split;  // 0: store hi = rna_tf32(x) explicitly; 1: leave x in place, the tensor core truncates; 2: rounds
     uint32_t tiles_m, tiles_n;
     int n_peers, self;
     float *peers[16];
 };
 
 struct Barriers {
-    uint64_t raw_full[STAGES];    // TMA -> converters
-    uint64_t conv_done[STAGES];   // converters -> MMA
-    uint64_t stage_free[STAGES];  // MMA (commit) -> TMA
-    uint64_t acc_full[2];         // MMA (commit) -> epilogue
-    uint64_t acc_empty[2];        // epilogue -> MMA
+    uint64_t raw_full[MAX_STAGES];    // TMA -> converters                      (own CTA)
+    uint64_t conv_done[MAX_STAGES];   // converters of both CTAs -> MMA         (leader CTA's copy is used)
+    uint64_t stage_free[MAX_STAGES];  // MMA (commit, multicast) -> TMA         (own CTA)
+    uint64_t acc_full[2];             // MMA (commit, multicast) -> epilogue    (own CTA)
+    uint64_t acc_empty[2];            // epilogue of both CTAs -> MMA           (leader CTA's copy is used)
     uint32_t tmem_base;
 };
 
@@ -72,13 +85,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+template <int CTAS> __device__ __forceinline__ void arrive_on_leader(uint64_t *bar) {
+    if (CTAS == 1) mbar_arrive(bar);
+    else mbar_arrive_cluster(bar, 0);
+}
+
+template <int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    using C = Cfg<CTAS>;
+    constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RAW_BYTES = C::RAW_BYTES, A_BYTES = C::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
+    // the dynamic smem base has the same CTA-relative offset in both CTAs of a pair, so the aligned tiles do too
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CTAS == 1 ? 0u : cluster_ctarank();
+    const uint32_t unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // a unit = one CTA or one CTA pair
     const uint32_t num_tiles = p.tiles_m * p.tiles_n;
     const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
 
@@ -87,29 +111,34 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&bars->raw_full[s], 1);
-            mbar_init(&bars->conv_done[s], CONV_WARPS);
+            mbar_init(&bars->conv_done[s], CONV_WARPS * CTAS);
             mbar_init(&bars->stage_free[s], 1);
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], EPI_WARPS);
+            mbar_init(&bars->acc_empty[a], EPI_WARPS * CTAS);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    if (warp == 1) {
+        if (CTAS == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+        else tmem_alloc_2cta(&bars->tmem_base, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 1) __syncthreads();
+    else cluster_sync_all();  // the peer's barriers must be initialised before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ================================================================= TMA producer
+        // ================================================================= TMA producer (every CTA, own operand halves)
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (uint32_t t = unit; t < num_tiles; t += n_units) {
                 uint32_t tm, tn;
                 tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-                const int32_t m0 = (int32_t)(tm * BM), n0 = (int32_t)(tn * BN);
+                const int32_t m0 = (int32_t)((tm * CTAS + rank) * BM);
+                const int32_t n0 = (int32_t)(tn * BN + rank * C::BN_LOAD);
                 for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->stage_free[s], ph ^ 1);
@@ -121,56 +150,71 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     } else {            // A[K][M]: four 32(m) x 32(k) boxes, MN-major
                         for (int j = 0; j < BM / 32; j++) tma_load_2d(a_dst + j * 4096, &tmA, m0 + 32 * j, k0, &bars->raw_full[s]);
                     }
-                    if (p.op_b == 1) {  // B[N][K]: one 32(k) x 256(n) box, K-major
+                    if (p.op_b == 1) {  // B[N][K]: one 32(k) x BN_LOAD(n) box, K-major
                         tma_load_2d(b_dst, &tmB, k0, n0, &bars->raw_full[s]);
-                    } else {            // B[K][N]: eight 32(n) x 32(k) boxes, MN-major
-                        for (int j = 0; j < BN / 32; j++) tma_load_2d(b_dst + j * 4096, &tmB, n0 + 32 * j, k0, &bars->raw_full[s]);
+                    } else {            // B[K][N]: 32(n) x 32(k) boxes, MN-major
+                        for (int j = 0; j < C::BN_LOAD / 32; j++) tma_load_2d(b_dst + j * 4096, &tmB, n0 + 32 * j, k0, &bars->raw_full[s]);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer
-        const uint32_t idesc = umma_idesc_tf32(BM, BN, p.op_a == 1, p.op_b == 0);
-        // K-major tile (SW128): 128-byte rows of 32 k, 8-row groups 1024 B apart (SBO).
-        // MN-major tile (SW128 with 32-byte atoms): 128-byte rows of 32 mn, one row per k, atoms of 4 k-rows = 512 B
-        // (SBO), 32-wide MN chunks 4096 B apart (LBO).
-        const uint64_t a_base = p.op_a == 0 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
-        const uint64_t b_base = p.op_b == 1 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
-        const uint32_t a_kstep = p.op_a == 0 ? 32 : 1024;  // bytes per k-step of 8
-        const uint32_t b_kstep = p.op_b == 1 ? 32 : 1024;
-        uint32_t it = 0, tile_i = 0;
-        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_i++) {
-            const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
-            mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&bars->conv_done[s], ph);
+        // ================================================================= MMA issuer (leader CTA only)
+        if (rank == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM * CTAS, BN, p.op_a == 1, p.op_b == 0);
+            // K-major tile (SW128): 128-byte rows of 32 k, 8-row groups 1024 B apart (SBO).
+            // MN-major tile (SW128 with 32-byte atoms): 128-byte rows of 32 mn, one row per k, atoms of 4 k-rows = 512 B
+            // (SBO), 32-wide MN chunks 4096 B apart (LBO).
+            const uint64_t a_base = p.op_a == 0 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
+            const uint64_t b_base = p.op_b == 1 ? umma_desc_base(16, 1024, UMMA_SW128) : umma_desc_base(4096, 512, UMMA_SW128_32B);
+            const uint32_t a_kstep = p.op_a == 0 ? 32 : 1024;  // bytes per k-step of 8
+            const uint32_t b_kstep = p.op_b == 1 ? 32 : 1024;
+            uint32_t it = 0, tile_i = 0;
+            for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
+                const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
+                mbar_wait<CTAS == 2>(&bars->acc_empty[acc], acc_ph ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
-                    const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = b_hi + RAW_BYTES;
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait<CTAS == 2>(&bars->conv_done[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
+                        const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = b_hi + RAW_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; k++) {
-                        const uint64_t dah = umma_desc(a_base, a_hi + k * a_kstep), dal = umma_desc(a_base, a_lo + k * a_kstep);
-                        const uint64_t dbh = umma_desc(b_base, b_hi + k * b_kstep), dbl = umma_desc(b_base, b_lo + k * b_kstep);
-                        mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) != 0);
-                        mma_tf32_ss(d_tmem, dah, dbl, idesc, 1);
-                        mma_tf32_ss(d_tmem, dah, dbh, idesc, 1);
+                        for (int k = 0; k < BK / 8; k++) {
+                            const uint64_t dah = umma_desc(a_base, a_hi + k * a_kstep), dal = umma_desc(a_base, a_lo + k * a_kstep);
+                            const uint64_t dbh = umma_desc(b_base, b_hi + k * b_kstep), dbl = umma_desc(b_base, b_lo + k * b_kstep);
+                            if (CTAS == 1) {
+                                mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+                                mma_tf32_ss(d_tmem, dah, dbl, idesc, 1);
+                                mma_tf32_ss(d_tmem, dah, dbh, idesc, 1);
+                            } else {
+                                mma_tf32_ss_2cta(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+                                mma_tf32_ss_2cta(d_tmem, dah, dbl, idesc, 1);
+                                mma_tf32_ss_2cta(d_tmem, dah, dbh, idesc, 1);
+                            }
+                        }
+                        // smem stage reusable (in both CTAs) once these MMAs retire; last k-block: accumulator complete
+                        if (CTAS == 1) {
+                            mma_commit(&bars->stage_free[s]);
+                            if (kb == num_kb - 1) mma_commit(&bars->acc_full[acc]);
+                        } else {
+                            mma_commit_2cta_multicast(&bars->stage_free[s], 3);
+                            if (kb == num_kb - 1) mma_commit_2cta_multicast(&bars->acc_full[acc], 3);
+                        }
                     }
-                    mma_commit(&bars->stage_free[s]);                       // smem stage reusable once these MMAs retire
-                    if (kb == num_kb - 1) mma_commit(&bars->acc_full[acc]);  // accumulator complete
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp < 2 + CONV_WARPS) {
         // ================================================================= converters: raw -> (hi, lo)
         const int ct = threadIdx.x - 64;  // 0..255
+        const int split = p.split;
         uint32_t it = 0;
-        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (uint32_t t = unit; t < num_tiles; t += n_units) {
             for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&bars->raw_full[s], ph);
@@ -180,13 +224,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int j = 0; j < RAW_BYTES / 16 / (CONV_WARPS * 32); j++) {
                     const int i = ct + j * (CONV_WARPS * 32);
                     const float4 x = hi[i];
-                    float4 h, l;
                     const float xs[4] = {x.x, x.y, x.z, x.w};
                     float hs[4], ls[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         uint32_t hb, lb;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs[e]));
+                        if (split == 1) hb = __float_as_uint(xs[e]) & 0xffffe000u;
+                        else asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs[e]));
                         const float hf = __uint_as_float(hb);
                         // inf - inf would poison the product: a non-finite hi carries the value alone
                         const float rem = (hb & 0x7f800000u) == 0x7f800000u ? 0.0f : xs[e] - hf;
@@ -194,28 +238,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         hs[e] = hf;
                         ls[e] = __uint_as_float(lb);
                     }
-                    h = make_float4(hs[0], hs[1], hs[2], hs[3]);
-                    l = make_float4(ls[0], ls[1], ls[2], ls[3]);
-                    hi[i] = h;
-                    lo[i] = l;
+                    if (split == 0) hi[i] = make_float4(hs[0], hs[1], hs[2], hs[3]);
+                    lo[i] = make_float4(ls[0], ls[1], ls[2], ls[3]);
                 }
-                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                // generic-proxy smem writes -> visible to the tensor core (async proxy), then release to the MMA warp
+                if (CTAS == 1) fence_proxy_async();
+                else fence_proxy_async_all();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->conv_done[s]);
+                if (lane == 0) arrive_on_leader<CTAS>(&bars->conv_done[s]);
             }
         }
     } else {
-        // ================================================================= epilogue
+        // ================================================================= epilogue (every CTA: its 128 rows x 256 columns)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         uint32_t tile_i = 0;
         const bool vec_ok = (p.ldc % 4 == 0);
-        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_i++) {
+        for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
             uint32_t tm, tn;
             tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
             const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
             mbar_wait(&bars->acc_full[acc], acc_ph);
             tc_fence_after();
-            const uint64_t row = (uint64_t)tm * BM + q * 32 + lane;
+            const uint64_t row = (uint64_t)(tm * CTAS + rank) * BM + q * 32 + lane;
             const uint64_t col0 = (uint64_t)tn * BN;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -226,7 +270,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                    if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
                 }
                 const uint64_t col = col0 + (uint64_t)c * 32;
                 if (row < p.M && col < p.N) {
@@ -280,14 +324,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 1) __syncthreads();
+    else cluster_sync_all();  // no CTA of a pair may exit (or free TMEM) while its partner can still touch it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CTAS == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+        else tmem_dealloc_2cta(tmem_base, TMEM_COLS);
     }
 }
 
 }  // namespace tc
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
 
 int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K, const float *alpha,
                     const float *A, uint64_t lda, const float *B, uint64_t ldb, const float *beta, float *C, uint64_t ldc,
@@ -302,11 +353,17 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         for (int i = 0; i < peers->n; i++)
             if (!aligned16(peers->ptrs[i])) return -1;
 
+    // CTA pairs (256 x 256 tiles) when the problem has at least two row tiles per pair to share; WK_GEMM_CTAS overrides
+    static const int ctas_env = env_int("WK_GEMM_CTAS", 0);
+    static const int split_env = env_int("WK_GEMM_SPLIT", 0);
+    const int ctas = ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1);
+    const uint32_t bn_load = BN / ctas;
+
     CUtensorMap tmA, tmB;
     bool ok;
     if (op_a == 0) ok = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, A, K, M, lda * 4, BK, BM);
     else ok = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, A, M, K, lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (op_b == 1) ok = ok && make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, B, K, N, ldb * 4, BK, BN);
+    if (op_b == 1) ok = ok && make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, B, K, N, ldb * 4, BK, bn_load);
     else ok = ok && make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, B, N, K, ldb * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (!ok) {
         set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed");
@@ -323,7 +380,8 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     p.bias = bias;
     p.act = act;
     p.op_a = op_a; p.op_b = op_b;
-    p.tiles_m = (uint32_t)((M + BM - 1) / BM);
+    p.split = split_env;
+    p.tiles_m = (uint32_t)((M + (uint64_t)BM * ctas - 1) / ((uint64_t)BM * ctas));
     p.tiles_n = (uint32_t)((N + BN - 1) / BN);
     p.n_peers = 0;
     p.self = 0;
@@ -335,12 +393,30 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
 
     static bool attr_set[64] = {false};
     if (!attr_set[q->device & 63]) {
-        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
         attr_set[q->device & 63] = true;
     }
     const uint64_t num_tiles = (uint64_t)p.tiles_m * p.tiles_n;
-    const unsigned grid = (unsigned)(num_tiles < (uint64_t)q->sm_count ? num_tiles : (uint64_t)q->sm_count);
-    gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, q->stream>>>(tmA, tmB, p);
+    const uint64_t max_units = (uint64_t)q->sm_count / ctas;
+    const unsigned units = (unsigned)(num_tiles < max_units ? num_tiles : max_units);
+    if (ctas == 1) {
+        gemm_tf32x3_kernel<1><<<units, THREADS, Cfg<1>::SMEM_BYTES, q->stream>>>(tmA, tmB, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(units * 2);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+        cfg.stream = q->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2>, tmA, tmB, p));
+    }
     WK_CHECK_LAUNCH();
     return WK_OK;
 }

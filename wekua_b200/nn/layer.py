@@ -3,6 +3,7 @@
 backward for the fused kernels (GEMM epilogue with bias + activation; act' * sensitivity in one pass)."""
 from __future__ import annotations
 
+import ctypes as C
 import math as _math
 
 import numpy as np
@@ -10,7 +11,7 @@ import numpy as np
 from .. import blas, capi
 from .. import math as wmath
 from ..core import Context, Pipeline
-from ..tensor import Tensor, fill, random
+from ..tensor import Tensor, _scalar, fill, random
 from .activation import ACT_NONE, Activation
 
 
@@ -121,6 +122,7 @@ class Linear:
                     pipeline.q, output.type_index, 0, 1, M, N, inp.shape[1], inp.ptr, inp.row_pitch, weight.ptr,
                     weight.row_pitch, output.ptr, output.row_pitch, self.bias[idx].ptr if self.bias_enabled else None,
                     self.activation.kind if self.activation else ACT_NONE))
+                self._fused_padding(pipeline, output, idx)
             else:
                 blas.gemm(pipeline, None, inp, blas.Operation.no_transpose, weight, blas.Operation.transpose, None, output, fwd_pt)
                 if self.bias_enabled:
@@ -129,6 +131,29 @@ class Linear:
                     self.activation.run(pipeline, output)
             inp = output
         return inp
+
+    def _fused_padding(self, pipeline, output: Tensor, idx: int):
+        """what the unfused sequence leaves in the padding of `output` (odd shapes only): the packed GEMM writes 0
+        there (gemm_pack.cl:89-91), bias.cl adds bias[i % row_pitch] over the whole buffer (bias.cl:3-19) and the
+        activation runs over the whole buffer (sigmoid.zig:62-80) -- reproduced so math.sum / mse see the same values"""
+        M, N = output.shape
+        if output.row_pitch == N and output.rows_padded == M:
+            return
+        blas.finish_c_padding(pipeline, output, None)
+        lib, q, ti, es = capi.lib(), pipeline.q, output.type_index, output.dtype.itemsize
+        act_op = {1: 6, 2: 5}.get(self.activation.kind) if self.activation is not None else None
+        if output.rows_padded > M:  # the pad row sees the logical bias values: act(0 + bias[j])
+            ptr = C.c_void_p(output.buffer + M * output.row_pitch * es)
+            n = (output.rows_padded - M) * output.row_pitch
+            if self.bias_enabled:
+                capi.check(lib.wk_bias_add(q, ti, ptr, self.bias[idx].ptr, output.row_pitch, n))
+            if act_op is not None:
+                capi.check(lib.wk_unary(q, ti, act_op, ptr, n))
+        if output.row_pitch > N and act_op is not None:  # pad column of the logical rows: act(0 + 0)
+            at_zero = 0.5 if self.activation.kind == 1 else 0.0
+            _, pv = _scalar(output.dtype, at_zero)
+            capi.check(lib.wk_fill(q, ti, 1, M, output.row_pitch - N, C.c_void_p(output.buffer + N * es),
+                                   output.row_pitch, output.slice_pitch, pv))
 
     def get_sensitivity(self, cache: LinearCache) -> Tensor:
         return cache.sensitivities[-1]
