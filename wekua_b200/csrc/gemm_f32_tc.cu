@@ -172,12 +172,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t it = 0, tile_i = 0;
             for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
                 const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
-                mbar_wait<CTAS == 2>(&bars->acc_empty[acc], acc_ph ^ 1);
+                mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait<CTAS == 2>(&bars->conv_done[s], ph);
+                    mbar_wait(&bars->conv_done[s], ph);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
@@ -242,8 +242,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     lo[i] = make_float4(ls[0], ls[1], ls[2], ls[3]);
                 }
                 // generic-proxy smem writes -> visible to the tensor core (async proxy), then release to the MMA warp
-                if (CTAS == 1) fence_proxy_async();
-                else fence_proxy_async_all();
+                fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) arrive_on_leader<CTAS>(&bars->conv_done[s]);
             }
@@ -355,7 +354,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
 
     // CTA pairs (256 x 256 tiles) when the problem has at least two row tiles per pair to share; WK_GEMM_CTAS overrides
     static const int ctas_env = env_int("WK_GEMM_CTAS", 0);
-    static const int split_env = env_int("WK_GEMM_SPLIT", 0);
+    static const int split_env = env_int("WK_GEMM_SPLIT", 1);
     const int ctas = ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1);
     const uint32_t bn_load = BN / ctas;
 

@@ -51,7 +51,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta_
     asm volatile(
         "{\n\t.reg .b32 r;\n\t"
         "mapa.shared::cluster.u32 r, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}\n" ::"r"(smem_u32(bar)),
+        "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}\n" ::"r"(smem_u32(bar)),
         "r"(cta_rank)
         : "memory");
 }
