@@ -1,8 +1,268 @@
-// placeholder until the DMMA kernel lands
+// gemm_f64_tc.cu -- f64 blas.gemm on the FP64 tensor-core instruction (DMMA, mma.sync.m16n8k4.f64).
+//
+//   C[M,N] = alpha * op(A) * op(B) + beta * C        (src/blas/gemm.zig:834-874, all four transpose pairs)
+//
+// Blackwell has no tcgen05 kind for f64: FP64 tensor work is the warp-level mma.sync with register accumulators.
+// Measured on this B200 (profiles/mma_peak_fp64_r01.txt) DMMA peaks at 37.0 TFLOP/s against 36.0 for plain DFMA,
+// i.e. the FP64 pipe itself is the ceiling and one m16n8k4 occupies a sub-partition's pipe for 32 cycles.  What DMMA
+// buys is issue slots: one instruction per 512 FMAs instead of one per 32, so the loads, address math and barriers
+// of a tiled kernel hide completely behind the pipe (the SIMT kernel, which needs every other issue slot for a DFMA,
+// stalls at 20 TFLOP/s).  The kernel is therefore a plain, deep, conflict-free pipeline:
+//
+//   CTA tile 128 x 128, k-block 16, 512 threads = 16 warps (4 x 4), warp tile 32 x 32 = 2 x 4 m16n8k4 tiles,
+//   64 accumulator registers per thread;
+//   global -> shared with 16-byte cp.async (zero fill at the edges), 4-stage ring, one __syncthreads per k-block;
+//   shared tiles padded to a pitch of 4 (mod 16) doubles so every fragment load (8 rows x 4 k) is conflict-free:
+//     k-contiguous operand (A not transposed / B transposed):  tile[mn][16 + 4]
+//     mn-contiguous operand (A transposed / B not transposed): tile[k][128 + 4]
+//   epilogue straight from registers: alpha/beta/bias/activation, 16-byte stores (and peer GPUs for the fused
+//   all-gather).
 #include "common.cuh"
+
 namespace wk {
-int32_t gemm_f64_tc(wk_queue *, int32_t, int32_t, uint64_t, uint64_t, uint64_t, const double *, const double *, uint64_t,
-                    const double *, uint64_t, const double *, double *, uint64_t, const double *, int32_t, const GemmPeers *) {
-    return -1;
+namespace dmma {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int THREADS = 512;
+constexpr int STAGES = 4;
+constexpr int PK = BK + 4;     // pitch of a k-contiguous tile row (doubles)
+constexpr int PMN = BM + 4;    // pitch of an mn-contiguous tile row (doubles)
+constexpr int TILE_DOUBLES = BM * PK > BK * PMN ? BM * PK : BK * PMN;  // 2560
+constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 160 KiB
+
+struct Params {
+    const double *A, *B;
+    double *C;
+    uint64_t M, N, K, lda, ldb, ldc;
+    double alpha, beta;
+    int has_alpha, has_beta;
+    const double *bias;
+    int act;
+    uint32_t tiles_m, tiles_n;
+    int n_peers, self;
+    double *peers[16];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_m16n8k4(double (&c)[4], double a0, double a1, double b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a0), "d"(a1), "d"(b0));
+}
+
+__device__ __forceinline__ double apply_act(double v, int act) {
+    if (act == WK_ACT_SIGMOID) return 1.0 / (1.0 + exp(-v));
+    if (act == WK_ACT_TANH) return tanh(v);
+    return v;
+}
+
+// One operand tile of a k-block into shared memory.  KCONTIG: stored [mn][k] (k contiguous in global memory) ->
+// tile[mn][PK]; else stored [k][mn] -> tile[k][PMN].  1024 16-byte chunks per tile, 2 per thread.
+template <bool KCONTIG>
+__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ g, uint64_t ld, uint64_t mn0, uint64_t mn_dim,
+                                          uint64_t k0, uint64_t k_dim) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int c = threadIdx.x + i * THREADS;
+        if (KCONTIG) {
+            const int r = c >> 3, kc = (c & 7) * 2;  // 128 rows x 8 chunks of 2 k
+            const uint64_t gm = mn0 + r, gk = k0 + kc;
+            int bytes = 0;
+            if (gm < mn_dim && gk < k_dim) bytes = gk + 1 < k_dim ? 16 : 8;
+            const double *src = bytes ? g + gm * ld + gk : g;
+            cp_async16(tile + r * PK + kc, src, bytes);
+        } else {
+            const int r = c >> 6, mc = (c & 63) * 2;  // 16 k-rows x 64 chunks of 2 mn
+            const uint64_t gk = k0 + r, gm = mn0 + mc;
+            int bytes = 0;
+            if (gk < k_dim && gm < mn_dim) bytes = gm + 1 < mn_dim ? 16 : 8;
+            const double *src = bytes ? g + gk * ld + gm : g;
+            cp_async16(tile + r * PMN + mc, src, bytes);
+        }
+    }
+}
+
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &tm, uint32_t &tn) {
+    // groups of 16 row-tiles sweep the columns together so the CTAs resident at the same time share panels in L2
+    constexpr uint32_t GM = 16;
+    const uint32_t per_group = GM * tiles_n;
+    const uint32_t group = t / per_group, in_group = t - group * per_group;
+    const uint32_t first_m = group * GM;
+    const uint32_t gsize = min(GM, tiles_m - first_m);
+    tm = first_m + in_group % gsize;
+    tn = in_group / gsize;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+
+    uint32_t tm, tn;
+    tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
+    const uint64_t m0 = (uint64_t)tm * BM, n0 = (uint64_t)tn * BN;
+    const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
+
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[i][j][e] = 0.0;
+
+    auto load_stage = [&](uint32_t kb) {
+        double *sa = smem + (kb % STAGES) * STAGE_DOUBLES, *sb = sa + TILE_DOUBLES;
+        load_tile<!TA>(sa, p.A, p.lda, m0, p.M, (uint64_t)kb * BK, p.K);
+        load_tile<TB>(sb, p.B, p.ldb, n0, p.N, (uint64_t)kb * BK, p.K);
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if ((uint32_t)s < num_kb) load_stage(s);
+        cp_async_commit();
+    }
+
+    for (uint32_t kb = 0; kb < num_kb; kb++) {
+        cp_async_wait<STAGES - 2>();  // this thread's part of stage kb has landed
+        __syncthreads();              // everyone's part has, and everyone is done reading stage kb-1
+        if (kb + STAGES - 1 < num_kb) load_stage(kb + STAGES - 1);  // refills the buffer stage kb-1 used
+        cp_async_commit();
+
+        const double *sa = smem + (kb % STAGES) * STAGE_DOUBLES, *sb = sa + TILE_DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[2][2], b[4];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (!TA) {  // tile[m][PK]
+                    a[i][0] = sa[(wm + i * 16 + g) * PK + kk + t];
+                    a[i][1] = sa[(wm + i * 16 + g + 8) * PK + kk + t];
+                } else {    // tile[k][PMN]
+                    a[i][0] = sa[(kk + t) * PMN + wm + i * 16 + g];
+                    a[i][1] = sa[(kk + t) * PMN + wm + i * 16 + g + 8];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!TB) b[j] = sb[(kk + t) * PMN + wn + j * 8 + g];  // tile[k][PMN]
+                else b[j] = sb[(wn + j * 8 + g) * PK + kk + t];       // tile[n][PK]
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m16n8k4(acc[i][j], a[i][0], a[i][1], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---------------------------------------------------------------- epilogue: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = row g+8
+    const bool vec_ok = (p.ldc % 2 == 0);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint64_t row = m0 + wm + i * 16 + g + h * 8;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t col = n0 + wn + j * 8 + 2 * t;
+                if (col >= p.N) continue;
+                double v0 = acc[i][j][h * 2], v1 = acc[i][j][h * 2 + 1];
+                double *cp = p.C + row * p.ldc + col;
+                const bool two = col + 1 < p.N;
+                if (p.has_alpha) { v0 *= p.alpha; v1 *= p.alpha; }
+                if (p.has_beta) {
+                    if (two && vec_ok) {
+                        const double2 o = *reinterpret_cast<const double2 *>(cp);
+                        v0 += p.beta * o.x; v1 += p.beta * o.y;
+                    } else {
+                        v0 += p.beta * cp[0];
+                        if (two) v1 += p.beta * cp[1];
+                    }
+                }
+                if (p.bias) {
+                    v0 += p.bias[col];
+                    if (two) v1 += p.bias[col + 1];
+                }
+                if (p.act) { v0 = apply_act(v0, p.act); v1 = apply_act(v1, p.act); }
+                if (two && vec_ok) {
+                    *reinterpret_cast<double2 *>(cp) = make_double2(v0, v1);
+                    for (int pi = 0; pi < p.n_peers; pi++)
+                        if (pi != p.self) *reinterpret_cast<double2 *>(p.peers[pi] + row * p.ldc + col) = make_double2(v0, v1);
+                } else {
+                    cp[0] = v0;
+                    if (two) cp[1] = v1;
+                    for (int pi = 0; pi < p.n_peers; pi++)
+                        if (pi != p.self) {
+                            p.peers[pi][row * p.ldc + col] = v0;
+                            if (two) p.peers[pi][row * p.ldc + col + 1] = v1;
+                        }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dmma
+
+int32_t gemm_f64_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K, const double *alpha,
+                    const double *A, uint64_t lda, const double *B, uint64_t ldb, const double *beta, double *C, uint64_t ldc,
+                    const double *bias, int32_t act, const GemmPeers *peers) {
+    using namespace dmma;
+    // cp.async moves 16-byte chunks: bases and row starts must be 16-byte aligned
+    if (!aligned16(A) || !aligned16(B) || (lda % 2) || (ldb % 2)) return -1;
+    if (q->prop.major < 9) return -1;
+
+    Params p{};
+    p.A = A; p.B = B; p.C = C;
+    p.M = M; p.N = N; p.K = K;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.has_alpha = (alpha != nullptr || beta != nullptr);
+    p.has_beta = (beta != nullptr);
+    p.alpha = alpha ? *alpha : 1.0;
+    p.beta = beta ? *beta : 0.0;
+    p.bias = bias;
+    p.act = act;
+    p.tiles_m = (uint32_t)((M + BM - 1) / BM);
+    p.tiles_n = (uint32_t)((N + BN - 1) / BN);
+    if ((uint64_t)p.tiles_m * p.tiles_n > 0x7fffffffULL) return -1;
+    p.n_peers = 0;
+    p.self = 0;
+    if (peers && peers->n > 1) {
+        p.n_peers = peers->n;
+        p.self = peers->self;
+        for (int i = 0; i < peers->n; i++) {
+            if (!aligned16(peers->ptrs[i])) return -1;
+            p.peers[i] = (double *)peers->ptrs[i];
+        }
+    }
+    if (!aligned16(C)) return -1;  // 16-byte epilogue accesses
+
+    static bool attr_set[64] = {false};
+    if (!attr_set[q->device & 63]) {
+        WK_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[q->device & 63] = true;
+    }
+    const unsigned grid = p.tiles_m * p.tiles_n;
+    if (op_a == 0 && op_b == 0) gemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
+    else if (op_a == 0 && op_b == 1) gemm_dmma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
+    else if (op_a == 1 && op_b == 0) gemm_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
+    else gemm_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
+
 }  // namespace wk
