@@ -11,7 +11,8 @@
 //
 //   CTA tile 128 x 128, k-block 16, 512 threads = 16 warps (4 x 4), warp tile 32 x 32 = 2 x 4 m16n8k4 tiles,
 //   64 accumulator registers per thread;
-//   global -> shared with 16-byte cp.async (zero fill at the edges), 4-stage ring, one __syncthreads per k-block;
+//   global -> shared with 16-byte cp.async (zero fill at the edges), 4-buffer ring filled 2 k-blocks ahead, full/empty
+//   mbarriers per buffer instead of a CTA-wide barrier (warps drift by up to a k-block without stalling each other);
 //   shared tiles padded to a pitch of 4 (mod 16) doubles so every fragment load (8 rows x 4 k) is conflict-free:
 //     k-contiguous operand (A not transposed / B transposed):  tile[mn][16 + 4]
 //     mn-contiguous operand (A transposed / B not transposed): tile[k][128 + 4]
@@ -25,6 +26,7 @@ namespace dmma {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int THREADS = 512;
 constexpr int STAGES = 4;
+constexpr int PREFETCH = 2;  // k-blocks in flight ahead of the one being multiplied
 constexpr int PK = BK + 4;     // pitch of a k-contiguous tile row (doubles)
 constexpr int PMN = BM + 4;    // pitch of an mn-contiguous tile row (doubles)
 constexpr int TILE_DOUBLES = BM * PK > BK * PMN ? BM * PK : BK * PMN;  // 2560
@@ -48,8 +50,32 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {  // bounded: a protocol bug traps instead of hanging
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > 4096) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 6000000000LL) __trap();
+        }
+    }
+}
 
 __device__ __forceinline__ void dmma_m16n8k4(double (&c)[4], double a0, double a1, double b0) {
     asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -126,22 +152,41 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
         load_tile<TB>(sb, p.B, p.ldb, n0, p.N, (uint64_t)kb * BK, p.K);
     };
 
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if ((uint32_t)s < num_kb) load_stage(s);
-        cp_async_commit();
+    // full[b]: every thread's cp.async of the stage in buffer b has landed (cp.async.mbarrier.arrive.noinc, 512 arrivals)
+    // empty[b]: all 16 warps are done reading buffer b.  A buffer is refilled PREFETCH = 2 k-blocks ahead, i.e. one
+    // whole k-block after its last reader started the next one, so no warp ever waits for a straggler: there is no
+    // CTA-wide barrier in the main loop (the __syncthreads version lost 14 % of its issue slots there,
+    // profiles/ncu_gemm_f64_r01a.txt).
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < STAGES; b++) {
+            mbar_init(&full_bar[b], THREADS);
+            mbar_init(&empty_bar[b], THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+
+    auto issue_stage = [&](uint32_t j) {  // k-block j -> buffer j % STAGES
+        const uint32_t b = j % STAGES, use = j / STAGES;
+        if (use > 0) mbar_wait(&empty_bar[b], (use - 1) & 1);
+        load_stage(j);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&full_bar[b]))
+                     : "memory");
+    };
+#pragma unroll
+    for (int j = 0; j < PREFETCH; j++)
+        if ((uint32_t)j < num_kb) issue_stage(j);
 
     for (uint32_t kb = 0; kb < num_kb; kb++) {
-        cp_async_wait<STAGES - 2>();  // this thread's part of stage kb has landed
-        __syncthreads();              // everyone's part has, and everyone is done reading stage kb-1
-        if (kb + STAGES - 1 < num_kb) load_stage(kb + STAGES - 1);  // refills the buffer stage kb-1 used
-        cp_async_commit();
+        if (kb + PREFETCH < num_kb) issue_stage(kb + PREFETCH);
+        const uint32_t b = kb % STAGES;
+        mbar_wait(&full_bar[b], (kb / STAGES) & 1);
 
-        const double *sa = smem + (kb % STAGES) * STAGE_DOUBLES, *sb = sa + TILE_DOUBLES;
+        const double *sa = smem + b * STAGE_DOUBLES, *sb = sa + TILE_DOUBLES;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double a[2][2], b[4];
+            double a[2][2], b_[4];
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 if (!TA) {  // tile[m][PK]
@@ -154,16 +199,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (!TB) b[j] = sb[(kk + t) * PMN + wn + j * 8 + g];  // tile[k][PMN]
-                else b[j] = sb[(wn + j * 8 + g) * PK + kk + t];       // tile[n][PK]
+                if (!TB) b_[j] = sb[(kk + t) * PMN + wn + j * 8 + g];  // tile[k][PMN]
+                else b_[j] = sb[(wn + j * 8 + g) * PK + kk + t];       // tile[n][PK]
             }
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma_m16n8k4(acc[i][j], a[i][0], a[i][1], b[j]);
+                for (int j = 0; j < 4; j++) dmma_m16n8k4(acc[i][j], a[i][0], a[i][1], b_[j]);
         }
+        __syncwarp();  // every lane's shared-memory reads of this buffer have been consumed by the MMAs above
+        if (lane == 0) mbar_arrive(&empty_bar[b]);
     }
-    cp_async_wait<0>();
 
     // ---------------------------------------------------------------- epilogue: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = row g+8
     const bool vec_ok = (p.ldc % 2 == 0);
