@@ -41,6 +41,9 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+FP64_DMMA_PEAK_TFLOPS = 37.04  # profiles/mma_peak_fp64_r01.txt
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)"""
@@ -208,8 +211,9 @@ def gemm_roofline(tflops, dtype, peaks, sustained, traffic=None):
         basis = (f"{peaks['_source']} cuBLAS bf16 {'sustained' if sustained else 'burst'} {bf16:.0f} TF/s / 2 (tf32 rate) / 3 "
                  "(3xTF32 passes per useful flop)")
     else:
-        peak = 40.0
-        basis = "B200 FP64 tensor-core spec 40 TF/s (no measured FP64 denominator in MEASURED_PEAKS.json)"
+        peak = FP64_DMMA_PEAK_TFLOPS
+        basis = ("DMMA m16n8k16 register-only loop measured on this pool's B200 by tools/mma_peak.cu "
+                 "(profiles/mma_peak_fp64_r01.txt; MEASURED_PEAKS.json has no FP64 entry; spec 40 TF/s)")
     return {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
             "traffic": traffic, "peak_basis": basis}
 
@@ -295,12 +299,15 @@ def run_ours(args):
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
-    # ---------------- resident operands: A row block, full B, full C (the gather target)
+    # ---------------- resident operands: A row block, full B, full C (the gather target, IPC-mapped on every peer)
+    from wekua_b200 import rowshard
+
     dt = np.float32
     a = wk.Tensor.alloc(ctx, pipe, (rows, N), dt)
     b = wk.Tensor.alloc(ctx, pipe, (N, N), dt)
-    c_full = wk.Tensor.alloc(ctx, pipe, (N, N), dt)
-    c_blk = wk.Tensor.wrap(ctx, pipe, (rows, N), dt, c_full.buffer + row0 * c_full.row_pitch * 4)
+    shard = rowshard.RowShardedC(ctx, pipe, N, N, dt, rank, world)
+    c_full = shard.c
+    c_blk = shard.block(pipe)
     # reference PRNG (uniform.cl); every rank seeds its own row block of A, B is identical everywhere
     wk.tensor.random.uniform(pipe, a, 42 + 1000 * rank, -1, 1)
     wk.tensor.random.uniform(pipe, b, 43, -1, 1)
@@ -308,35 +315,68 @@ def run_ours(args):
 
     gather = args.gather if world > 1 else "none"
     c_torch = None
-    if gather == "nccl":
+    if world > 1:
         class _Cai:
             __cuda_array_interface__ = {"shape": (N * c_full.row_pitch,), "typestr": "<f4", "data": (c_full.buffer, False),
                                         "version": 3}
         c_torch = torch.as_tensor(_Cai(), device=f"cuda:{local_rank}")
 
-    def step():
-        wk.blas.gemm(pipe, None, a, 0, b, 0, None, c_blk)
-        if gather == "nccl":
-            pipe.command_queue.finish()
-            chunk = (N // g) * c_full.row_pitch
-            torch.distributed.all_gather_into_tensor(c_torch[: chunk * g], c_torch[rank * chunk:(rank + 1) * chunk])
-            torch.cuda.synchronize()
+    def make_step(mode):
+        def step():
+            if mode == "fused":  # the GEMM epilogue stores every C tile to all peers over NVLink: no collective
+                shard.gemm(pipe, None, a, 0, b, 0, None)
+            else:
+                wk.blas.gemm(pipe, None, a, 0, b, 0, None, c_blk)
+                if mode == "nccl":
+                    pipe.command_queue.finish()
+                    chunk = (N // g) * c_full.row_pitch
+                    torch.distributed.all_gather_into_tensor(c_torch[: chunk * g], c_torch[rank * chunk:(rank + 1) * chunk])
+                    torch.cuda.synchronize()
+        return step
 
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=f"cuda:{local_rank}", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    step = make_step(gather)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms, launches, t0, t1 = timed(wk, pipe, step, args.steps, args.warmup, barrier)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms = max_over_ranks(ms)
     if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
         lt = torch.tensor([launches], device=f"cuda:{local_rank}", dtype=torch.int64)
         torch.distributed.all_reduce(lt)
         launches = int(lt.item())
     flops = 2.0 * N * N * N
     tflops = flops * args.steps / (ms * 1e-3) / 1e12
     per_gpu_tflops = tflops / g
+
+    # the other two ways of finishing the step (reported beside the headline), and a check that the gathered C is the
+    # same matrix on every rank: the deterministic two-stage sum of the full C must agree bit for bit
+    variants, gather_check = {}, None
+    if world > 1:
+        for mode in ("none", "nccl", "fused"):
+            if mode == gather:
+                continue
+            vms, _, _, _ = timed(wk, pipe, make_step(mode), max(2, args.steps // 2), 2, barrier)
+            vms = max_over_ranks(vms)
+            variants[mode] = flops * max(2, args.steps // 2) / (vms * 1e-3) / 1e12
+        wk.capi.check(wk.capi.lib().wk_memset_zero(pipe.q, c_full.ptr, c_full.size))
+        pipe.wait_and_cleanup()
+        barrier()
+        make_step("fused")()
+        pipe.wait_and_cleanup()
+        barrier()
+        total = float(wk.math.sum(pipe, c_full))
+        blk = float(wk.math.sum(pipe, c_blk))
+        sums = rowshard.exchange((total, blk), world)
+        gather_check = bool(all(s_[0] == sums[0][0] for s_ in sums) and np.isfinite(total)
+                            and abs(sum(s_[1] for s_ in sums) - total) <= 1e-3 * max(1.0, abs(total)))
 
     # ---------------- e2e: same product through the public API from HOST buffers (pinned), copies inside the region
     e2e = None
@@ -350,22 +390,22 @@ def run_ours(args):
         def e2e_step():
             wk.tensor.memory.read_from_buffer(pipe, a, ha)
             wk.tensor.memory.read_from_buffer(pipe, b, hb)
-            wk.blas.gemm(pipe, None, a, 0, b, 0, None, c_blk)
+            make_step("fused" if gather == "fused" else "none")()
             wk.tensor.memory.write_to_buffer(pipe, c_blk, hc.reshape(-1))
 
         e_steps = max(1, min(args.steps, 3))
         ems, _, _, _ = timed(wk, pipe, e2e_step, e_steps, 1, barrier)
-        if world > 1:
-            t = torch.tensor([ems], device=f"cuda:{local_rank}", dtype=torch.float64)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ems = float(t.item())
+        ems = max_over_ranks(ems)
         e2e = {"value": flops * e_steps / (ems * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int((rows * N + N * N) * 4 * g), "d2h_bytes_per_step": int(N * N * 4),
                "steps": e_steps, "ms_per_step": ems / e_steps}
         for p in (pa, pb, pc):
             wk.capi.lib().wk_host_free(p)
-    for t_ in (a, b, c_full):
+    for t_ in (a, b):
         t_.release(pipe)
+    if world > 1:
+        barrier()  # nobody unmaps a peer's C while that peer may still be storing into it
+    shard.release(pipe)
 
     # ---------------- secondary configs + cpu baseline (rank 0, N = 1 only)
     also, cpu = [], None
@@ -394,6 +434,9 @@ def run_ours(args):
             "roofline": gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True),
             "cpu_baseline": cpu, "also": also,
         }
+        if world > 1:
+            line["gather_variants_tflops"] = variants
+            line["gather_check"] = gather_check
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -408,7 +451,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=32768)
     ap.add_argument("--ref-n", type=int, default=4096, dest="ref_n")
-    ap.add_argument("--gather", default="nccl", choices=["none", "nccl", "fused"])
+    ap.add_argument("--gather", default="fused", choices=["none", "nccl", "fused"])
     ap.add_argument("--quick", action="store_true", help="headline line only (no secondary configs)")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")

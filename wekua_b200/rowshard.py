@@ -1,0 +1,120 @@
+"""Row-sharded multi-GPU GEMM (BASELINE config 5).
+
+The reference's multi-device mode is "one CommandQueue per device" (src/core/command_queue.zig:160-181): no op ever
+splits work.  Here the split is explicit: C[M,N] = alpha*op(A)*op(B) + beta*C is partitioned into `world` contiguous
+row blocks of op(A) and C, B is replicated, every rank (one process per GPU) computes its block with no
+communication, and the blocks are reassembled on every GPU by the GEMM epilogue itself: each finished 16-byte piece
+of C is stored into the rank's own buffer AND into every peer's buffer through CUDA-IPC mapped pointers, so the NVLink
+transfer overlaps the tensor-core work tile by tile (wk_gemm_rowshard_allgather).  The host logic here -- the
+partition, the view of A a rank owns, the handle exchange -- is pure Python and covered by world_size-2 gloo tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .tensor import Tensor, _scalar
+
+
+def shard_rows(m: int, world: int, rank: int) -> tuple[int, int]:
+    """(row0, rows) of rank's contiguous block of the M rows: M // world rows each, the last rank takes the rest"""
+    if world < 1 or not 0 <= rank < world or m < world:
+        raise capi.InvalidValue(f"InvalidValue: cannot shard {m} rows over {world} ranks (rank {rank})")
+    base = m // world
+    row0 = rank * base
+    return row0, (m - row0 if rank == world - 1 else base)
+
+
+def a_block(op_a: int, row0: int, rows: int, k: int, lda: int) -> tuple[int, tuple[int, int]]:
+    """(element offset into the stored A, stored shape) of the part of A that produces C rows [row0, row0+rows).
+    op_a = N: A is [M,K] -> rows row0.. of it (a row block).  op_a = T: A is [K,M] -> columns row0.. (a column block
+    with the same pitch: a strided view, no copy)."""
+    if op_a == 0:
+        return row0 * lda, (rows, k)
+    return row0, (k, rows)
+
+
+def exchange(obj, world: int, all_gather_object=None) -> list:
+    """every rank's `obj`, in rank order.  `all_gather_object(out_list, obj)` is torch.distributed's by default."""
+    out = [None] * world
+    if world == 1:
+        out[0] = obj
+        return out
+    if all_gather_object is None:
+        import torch.distributed as dist
+
+        all_gather_object = dist.all_gather_object
+    all_gather_object(out, obj)
+    return out
+
+
+class RowShardedC:
+    """The full-size result matrix of one rank plus the peers' copies, mapped through CUDA IPC."""
+
+    def __init__(self, context, pipeline, m: int, n: int, dtype, rank: int, world: int, all_gather_object=None):
+        self.context, self.rank, self.world = context, rank, world
+        self.m, self.n = m, n
+        self.row0, self.rows = shard_rows(m, world, rank)
+        self.c = Tensor.alloc(context, pipeline, (m, n), dtype)
+        pipeline.wait_and_cleanup()
+        lib = capi.lib()
+        self._opened = []
+        self.peer_ptrs = (C.c_void_p * world)()
+        if world == 1:
+            self.peer_ptrs[0] = self.c.buffer
+            return
+        handle = (C.c_ubyte * 64)()
+        capi.check(lib.wk_ipc_get_handle(pipeline.q, self.c.ptr, handle))
+        handles = exchange(bytes(handle), world, all_gather_object)
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.peer_ptrs[r] = self.c.buffer
+                continue
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            p = C.c_void_p()
+            capi.check(lib.wk_ipc_open_handle(pipeline.q, buf, C.byref(p)))
+            self.peer_ptrs[r] = p.value
+            self._opened.append(p)
+
+    def block(self, pipeline) -> Tensor:
+        """view of this rank's row block of C"""
+        off = self.row0 * self.c.row_pitch * self.c.dtype.itemsize
+        return Tensor.wrap(self.context, pipeline, (self.rows, self.n), self.c.dtype, self.c.buffer + off)
+
+    def gemm(self, pipeline, alpha, a_blk: Tensor, op_a: int, b: Tensor, op_b: int, beta) -> None:
+        """this rank's rows of C = alpha*op(A)*op(B) + beta*C, written to every rank's C.  `a_blk` is the rank's block
+        of A (see a_block).  Results are complete on all ranks after every rank's queue has finished + a barrier."""
+        k = a_blk.shape[1 - op_a]
+        rows = a_blk.shape[op_a]
+        if rows != self.rows or b.shape[op_b] != k or b.shape[1 - op_b] != self.n or a_blk.dtype != self.c.dtype:
+            raise capi.InvalidValue("InvalidValue: block shapes do not match the sharded C")
+        _, pal = _scalar(self.c.dtype, alpha)
+        _, pbe = _scalar(self.c.dtype, beta)
+        capi.check(capi.lib().wk_gemm_rowshard_allgather(
+            pipeline.q, self.c.type_index, op_a, op_b, self.rows, self.n, k, pal, a_blk.ptr, a_blk.row_pitch, b.ptr,
+            b.row_pitch, pbe, self.row0, self.peer_ptrs, self.world, self.rank, self.c.row_pitch))
+
+    def release(self, pipeline) -> None:
+        pipeline.wait_and_cleanup()
+        for p in self._opened:
+            capi.check(capi.lib().wk_ipc_close_handle(pipeline.q, p))
+        self._opened = []
+        self.c.release(pipeline)
+
+
+def reference_product(a: np.ndarray, op_a: int, b: np.ndarray, op_b: int, world: int) -> np.ndarray:
+    """numpy model of the sharded product (used by the CPU tests of the partition logic): concatenation of the
+    per-rank blocks computed from the a_block views"""
+    A = a.T if op_a else a
+    m, k = A.shape
+    lda = a.shape[1]
+    flat = a.reshape(-1)
+    blocks = []
+    for r in range(world):
+        row0, rows = shard_rows(m, world, r)
+        off, shape = a_block(op_a, row0, rows, k, lda)
+        view = np.lib.stride_tricks.as_strided(flat[off:], shape=shape, strides=(lda * a.itemsize, a.itemsize))
+        blocks.append((view.T if op_a else view) @ (b.T if op_b else b))
+    return np.concatenate(blocks, axis=0)

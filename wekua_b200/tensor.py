@@ -104,9 +104,17 @@ class Tensor:
         return t
 
     @classmethod
-    def wrap(cls, context, pipeline, shape, dtype, device_ptr: int) -> "Tensor":
-        """view over device memory someone else owns (e.g. a torch tensor's data_ptr()) with this layout"""
-        return cls.empty(context, pipeline, shape, dtype, True, _external_ptr=device_ptr)
+    def wrap(cls, context, pipeline, shape, dtype, device_ptr: int, row_pitch: int | None = None) -> "Tensor":
+        """view over device memory someone else owns (a row / column block of a larger tensor) with this layout;
+        `row_pitch` (elements) overrides the pitch the shape alone would give, for column blocks of a wider matrix"""
+        t = cls.empty(context, pipeline, shape, dtype, True, _external_ptr=device_ptr)
+        if row_pitch is not None:
+            if len(t.shape) != 2 or row_pitch < t.shape[1]:
+                raise capi.InvalidValue("InvalidValue: row_pitch override needs a 2-D view and pitch >= cols")
+            t.row_pitch = t.row_pitch_for_vectors = int(row_pitch)
+            t.slice_pitch = t.slice_pitch_for_vectors = t.row_pitch * t.rows_padded
+            t.pitches[0] = t.row_pitch
+        return t
 
     def release(self, pipeline: Pipeline) -> None:
         if self.buffer is not None and self._owns:
