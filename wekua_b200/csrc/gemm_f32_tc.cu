@@ -34,6 +34,8 @@ constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
 constexpr int THREADS = (2 + CONV_WARPS + EPI_WARPS) * 32;  // 448
 constexpr int TMEM_COLS = 512;                               // two 128x256 fp32 accumulators
 constexpr int MAX_STAGES = 3;
+constexpr int EPI_PITCH = 36;                                // floats per row of the epilogue transpose tile (32 + 4)
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;    // 18 KiB
 
 template <int CTAS> struct Cfg {
     static constexpr int BN_LOAD = BN / CTAS;          // B columns staged by each CTA
@@ -42,7 +44,7 @@ template <int CTAS> struct Cfg {
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;  // hi tiles (TMA lands here)
     static constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // + lo tiles
     static constexpr int STAGES = CTAS == 1 ? 2 : 3;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 struct Params {
@@ -250,6 +252,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ================================================================= epilogue (every CTA: its 128 rows x 256 columns)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        float *epi = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256) + q * 32 * EPI_PITCH;
         uint32_t tile_i = 0;
         const bool vec_ok = (p.ldc % 4 == 0);
         for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
@@ -258,7 +261,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
             mbar_wait(&bars->acc_full[acc], acc_ph);
             tc_fence_after();
-            const uint64_t row = (uint64_t)(tm * CTAS + rank) * BM + q * 32 + lane;
+            const uint64_t row0 = (uint64_t)(tm * CTAS + rank) * BM + q * 32;
             const uint64_t col0 = (uint64_t)tn * BN;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -271,53 +274,63 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     __syncwarp();
                     if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
                 }
-                const uint64_t col = col0 + (uint64_t)c * 32;
-                if (row < p.M && col < p.N) {
-                    float *crow = p.C + row * p.ldc + col;
-                    const bool full = vec_ok && (col + 32 <= p.N);
+                // TMEM hands every lane one ROW (32 columns); global memory wants every warp instruction to cover whole
+                // 128-byte row segments (local HBM sectors and, for the fused all-gather, NVLink packets).  Transpose the
+                // 32 x 32 chunk through a padded per-warp shared-memory tile: 16-byte writes at a 144-byte row pitch and
+                // 16-byte reads of 8 lanes per row are both conflict-free.
+                float4 *my_row = reinterpret_cast<float4 *>(epi + lane * EPI_PITCH);
 #pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        float v[4];
+                for (int g = 0; g < 8; g++)
+                    my_row[g] = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
+                                            __uint_as_float(r[g * 4 + 3]));
+                __syncwarp();
+                const uint64_t col = col0 + (uint64_t)c * 32 + (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int rl = it * 4 + (lane >> 3);
+                    const uint64_t row = row0 + rl;
+                    if (row >= p.M || col >= p.N) continue;
+                    const float4 a4 = *reinterpret_cast<const float4 *>(epi + rl * EPI_PITCH + (lane & 7) * 4);
+                    float v[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float *cp = p.C + row * p.ldc + col;
+                    const bool full = vec_ok && (col + 4 <= p.N);
+                    if (p.has_alpha) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) v[e] *= p.alpha;
+                    }
+                    if (full) {
+                        if (p.has_beta) {
+                            const float4 o = *reinterpret_cast<const float4 *>(cp);
+                            v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
+                        }
+                        if (p.bias) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(p.bias + col);
+                            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+                        }
+                        if (p.act) {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) v[e] = apply_act(v[e], p.act);
+                        }
+                        const float4 out = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4 *>(cp) = out;
+                        for (int pi = 0; pi < p.n_peers; pi++)
+                            if (pi != p.self) *reinterpret_cast<float4 *>(p.peers[pi] + row * p.ldc + col) = out;
+                    } else {
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            v[e] = __uint_as_float(r[g * 4 + e]);
-                            if (p.has_alpha) v[e] *= p.alpha;
-                        }
-                        if (full) {
-                            if (p.has_beta) {
-                                const float4 o = *reinterpret_cast<const float4 *>(crow + g * 4);
-                                v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
-                            }
-                            if (p.bias) {
-                                const float4 bv = *reinterpret_cast<const float4 *>(p.bias + col + g * 4);
-                                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-                            }
-                            if (p.act) {
-#pragma unroll
-                                for (int e = 0; e < 4; e++) v[e] = apply_act(v[e], p.act);
-                            }
-                            const float4 out = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4 *>(crow + g * 4) = out;
-                            for (int pi = 0; pi < p.n_peers; pi++)
-                                if (pi != p.self)
-                                    *reinterpret_cast<float4 *>(p.peers[pi] + row * p.ldc + col + g * 4) = out;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const uint64_t cc = col + g * 4 + e;
-                                if (cc < p.N) {
-                                    float o = v[e];
-                                    if (p.has_beta) o += p.beta * crow[g * 4 + e];
-                                    if (p.bias) o += p.bias[cc];
-                                    o = apply_act(o, p.act);
-                                    crow[g * 4 + e] = o;
-                                    for (int pi = 0; pi < p.n_peers; pi++)
-                                        if (pi != p.self) p.peers[pi][row * p.ldc + cc] = o;
-                                }
+                            if (col + e < p.N) {
+                                float o = v[e];
+                                if (p.has_beta) o += p.beta * cp[e];
+                                if (p.bias) o += p.bias[col + e];
+                                o = apply_act(o, p.act);
+                                cp[e] = o;
+                                for (int pi = 0; pi < p.n_peers; pi++)
+                                    if (pi != p.self) p.peers[pi][row * p.ldc + col + e] = o;
                             }
                         }
                     }
                 }
+                __syncwarp();  // the tile is overwritten by the next chunk
             }
         }
     }
