@@ -42,6 +42,13 @@ def measured_peaks():
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.04  # profiles/mma_peak_fp64_r01.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture of each kernel on B200
+NCU_TRAFFIC_BYTES = {
+    "gemm_f32_n32768_1gpu": 167.3e9,  # profiles/ncu_gemm_f32_r01c_n32768.txt (algorithmic A+B+C = 12.9e9; the
+    #                                   output-stationary bound for 74 resident 256x256 accumulators is ~150e9)
+    "axpy_f32_2^28": 3.176e9,         # profiles/ncu_axpy_f32_r01.txt (algorithmic 3.221e9)
+    "axpy_f64_2^28": 6.400e9,         # profiles/ncu_axpy_f64_r01.txt (algorithmic 6.442e9)
+}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -250,7 +257,8 @@ def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks):
     return {"metric": f"axpy_{name}_gbs", "value": gbs, "unit": "GB/s", "ms_per_step": ms / steps, "dtype": name,
             "config": {"workload": f"{name} axpy, 2^{int(np.log2(n))} elements, alternating x/y (benchmark/axpy.zig)",
                        "l2": "inputs_exceed_l2"},
-            "gpu_launches": launches, "roofline": hbm_roofline(gbs, peaks)}
+            "gpu_launches": launches,
+            "roofline": hbm_roofline(gbs, peaks, NCU_TRAFFIC_BYTES.get(f"axpy_{name}_2^{int(np.log2(n))}"))}
 
 
 def bench_gemm_single(wk, ctx, pipe, dtype, n, steps, warmup, peaks, op_a=0, op_b=0):
@@ -431,7 +439,8 @@ def run_ours(args):
                                    f"(BASELINE config 5); gather={gather}",
                        "N": N, "parallelism": f"rowshard{g}", "l2": "inputs_exceed_l2", "arith": "3xTF32 tcgen05, fp32 accumulate"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True),
+            "roofline": gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True,
+                                      traffic=NCU_TRAFFIC_BYTES["gemm_f32_n32768_1gpu"] if (g == 1 and N == 32768) else None),
             "cpu_baseline": cpu, "also": also,
         }
         if world > 1:

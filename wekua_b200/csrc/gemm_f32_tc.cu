@@ -56,7 +56,7 @@ struct Params {
     int act;
     int op_a, op_b;
     int split;  // 0: store hi = rna_tf32(x) explicitly; 1: leave x in place, the tensor core truncates; 2: rounds
-    uint32_t tiles_m, tiles_n;
+    uint32_t tiles_m, tiles_n, group_m;
     int n_peers, self;
     float *peers[16];
 };
@@ -70,9 +70,8 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t &tm, uint32_t &tn) {
-    // groups of 8 row-tiles sweep the columns together so concurrently resident tiles share A and B panels in L2
-    constexpr uint32_t GM = 8;
+__device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t GM, uint32_t &tm, uint32_t &tn) {
+    // groups of GM row-tiles sweep the columns together so concurrently resident tiles share A and B panels in L2
     const uint32_t per_group = GM * tiles_n;
     const uint32_t group = t / per_group, in_group = t - group * per_group;
     const uint32_t first_m = group * GM;
@@ -138,7 +137,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t it = 0;
             for (uint32_t t = unit; t < num_tiles; t += n_units) {
                 uint32_t tm, tn;
-                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+                tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
                 const int32_t m0 = (int32_t)((tm * CTAS + rank) * BM);
                 const int32_t n0 = (int32_t)(tn * BN + rank * C::BN_LOAD);
                 for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
@@ -257,7 +256,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const bool vec_ok = (p.ldc % 4 == 0);
         for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
             uint32_t tm, tn;
-            tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+            tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
             const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
             mbar_wait(&bars->acc_full[acc], acc_ph);
             tc_fence_after();
@@ -395,6 +394,8 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     p.split = split_env;
     p.tiles_m = (uint32_t)((M + (uint64_t)BM * ctas - 1) / ((uint64_t)BM * ctas));
     p.tiles_n = (uint32_t)((N + BN - 1) / BN);
+    static const int gm_env = env_int("WK_GEMM_GM", 16);
+    p.group_m = gm_env > 0 ? gm_env : 16;
     p.n_peers = 0;
     p.self = 0;
     if (peers && peers->n > 1) {
