@@ -69,3 +69,37 @@ def test_xor_training_matches_oracle(oracle, dtype, fused):
     opt.deinit(pipe)
     cache.deinit(pipe)
     seq.deinit(pipe)
+
+
+def test_cpp_host_mirror_xor_example_matches_python_path(oracle):
+    """examples/xor_neural_network.cpp (the reference's example against include/wekua.hpp) issues the same C-ABI call
+    sequence as the Python mirror: with the same weight seeds its final outputs are the same numbers, and it learns XOR."""
+    import os
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "bin", "xor_neural_network")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "examples")], check=True, capture_output=True)
+    r = subprocess.run([exe, "42"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"output:\s+\[([^\]]+)\]", r.stdout)
+    got = np.array([float(v) for v in m.group(1).split(",")])
+    assert np.all(np.abs(got - TARGETS.reshape(-1)) < 0.2), r.stdout
+    assert int(re.search(r"kernel launches: (\d+)", r.stdout).group(1)) > 300 * 10
+
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    inputs, expected, seq, layers, cache, opt = _build(wk, ctx, pipe, np.float32, (42, 43), False)
+    layer_cache = cache.get_layer_cache(0)
+    for _ in range(300):
+        output = layers.forward(pipe, inputs, layer_cache)
+        wk.nn.mse(pipe, output, expected, cache, calculate_derivative=True)
+        layers.backward(pipe, layer_cache, inputs, None)
+        opt.step(pipe, cache)
+    out = gh.to_np(layers.forward(pipe, inputs, layer_cache)).reshape(-1)
+    np.testing.assert_allclose(got, out, rtol=0, atol=2e-6)  # printed with 6 decimals
+    opt.deinit(pipe)
+    cache.deinit(pipe)
+    seq.deinit(pipe)
