@@ -165,6 +165,16 @@ class Pipeline:
         capi.check(capi.lib().wk_event_record(self.q, C.byref(ev)))
         self._events.append(ev)
 
+    def record_event(self):
+        """the event the last enqueue returned (cl_event out-parameter of clEnqueue*); owned by this pipeline"""
+        self.append()
+        return self._events[-1]
+
+    def wait_for(self, event) -> None:
+        """make everything enqueued on this pipeline from now on wait for `event` of ANOTHER pipeline -- the
+        wait-list argument of clEnqueue* (pipeline.prevEvents), for copy / compute overlap across queues"""
+        capi.check(capi.lib().wk_queue_wait_event(self.q, event))
+
     def wait_and_cleanup(self) -> None:
         capi.check(capi.lib().wk_queue_finish(self.q))
         self.clear()
