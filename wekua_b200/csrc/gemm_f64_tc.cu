@@ -11,7 +11,7 @@
 //
 //   CTA tile 128 x 128, k-block 16, 512 threads = 16 warps (4 x 4), warp tile 32 x 32 = 2 x 4 m16n8k4 tiles,
 //   64 accumulator registers per thread;
-//   global -> shared with 16-byte cp.async (zero fill at the edges), 4-buffer ring filled 2 k-blocks ahead, full/empty
+//   global -> shared with 16-byte cp.async (zero fill at the edges), 4-buffer ring filled one k-block ahead (measured best of the depth sweep), full/empty
 //   mbarriers per buffer instead of a CTA-wide barrier (warps drift by up to a k-block without stalling each other);
 //   shared tiles padded to a pitch of 4 (mod 16) doubles so every fragment load (8 rows x 4 k) is conflict-free:
 //     k-contiguous operand (A not transposed / B transposed):  tile[mn][16 + 4]
@@ -25,8 +25,14 @@ namespace dmma {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int THREADS = 512;
-constexpr int STAGES = 4;
-constexpr int PREFETCH = 2;  // k-blocks in flight ahead of the one being multiplied
+#ifndef WK_F64_STAGES
+#define WK_F64_STAGES 4
+#endif
+#ifndef WK_F64_PREFETCH
+#define WK_F64_PREFETCH 1
+#endif
+constexpr int STAGES = WK_F64_STAGES;
+constexpr int PREFETCH = WK_F64_PREFETCH;  // k-blocks in flight ahead of the one being multiplied
 constexpr int PK = BK + 4;     // pitch of a k-contiguous tile row (doubles)
 constexpr int PMN = BM + 4;    // pitch of an mn-contiguous tile row (doubles)
 constexpr int TILE_DOUBLES = BM * PK > BK * PMN ? BM * PK : BK * PMN;  // 2560
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
     };
 
     // full[b]: every thread's cp.async of the stage in buffer b has landed (cp.async.mbarrier.arrive.noinc, 512 arrivals)
-    // empty[b]: all 16 warps are done reading buffer b.  A buffer is refilled PREFETCH = 2 k-blocks ahead, i.e. one
+    // empty[b]: all 16 warps are done reading buffer b.  A buffer is refilled PREFETCH k-blocks ahead, i.e. at least one
     // whole k-block after its last reader started the next one, so no warp ever waits for a straggler: there is no
     // CTA-wide barrier in the main loop (the __syncthreads version lost 14 % of its issue slots there,
     // profiles/ncu_gemm_f64_r01a.txt).
