@@ -108,6 +108,19 @@ struct Context {  // src/core/context.zig:13-190
     }
 };
 
+struct Graph {  // a captured op sequence: launch() replays it as ONE launch (launch-bound layer steps)
+    wk_graph *handle = nullptr;
+    explicit Graph(wk_graph *g) : handle(g) {}
+    Graph(const Graph &) = delete;
+    Graph &operator=(const Graph &) = delete;
+    ~Graph() { wk_graph_release(handle); }
+    uint64_t numKernels() const {
+        uint64_t n = 0;
+        check(wk_graph_num_kernels(handle, &n));
+        return n;
+    }
+};
+
 struct Pipeline {  // src/core/pipeline.zig:6-66: the in-order CUDA stream IS the prevEvents -> append chain
     CommandQueue *command_queue;
     explicit Pipeline(CommandQueue *q) : command_queue(q) {}
@@ -116,6 +129,13 @@ struct Pipeline {  // src/core/pipeline.zig:6-66: the in-order CUDA stream IS th
     void prealloc(size_t) {}
     void waitAndCleanup() { command_queue->finish(); }
     void clear() {}
+    void beginCapture() { check(wk_graph_begin_capture(q())); }
+    std::unique_ptr<Graph> endCapture() {
+        wk_graph *g = nullptr;
+        check(wk_graph_end_capture(q(), &g));
+        return std::unique_ptr<Graph>(new Graph(g));
+    }
+    void launch(const Graph &g) { check(wk_graph_launch(g.handle, q())); }
 };
 }  // namespace core
 using core::CommandQueue;

@@ -101,6 +101,17 @@ int32_t wk_event_wait(wk_event *ev);                       /* cl.event.wait */
 int32_t wk_event_elapsed_ms(wk_event *start, wk_event *end, float *ms);
 int32_t wk_event_release(wk_event *ev);                    /* cl.event.release */
 
+/* CUDA-graph capture of a launch-bound op sequence (one Linear step is ~25 microsecond kernels; the
+ * reference pays one clEnqueueNDRangeKernel per op, src/core/pipeline.zig:35-45).  Ops enqueued on `q` between begin
+ * and end are recorded, not executed; wk_graph_launch replays them as one launch.  Blocking entries (wk_sum,
+ * wk_dot_reduce, wk_get_value, wk_free) must not be called while capturing. */
+typedef struct wk_graph wk_graph;
+int32_t wk_graph_begin_capture(wk_queue *q);
+int32_t wk_graph_end_capture(wk_queue *q, wk_graph **out);
+int32_t wk_graph_launch(wk_graph *g, wk_queue *q);
+int32_t wk_graph_num_kernels(const wk_graph *g, uint64_t *n);
+int32_t wk_graph_release(wk_graph *g);
+
 /* ------------------------------------------------------------------------------------------ memory */
 int32_t wk_malloc(wk_queue *q, size_t bytes, void **dptr);  /* cl.buffer.create, src/tensor/main.zig:241-247 */
 int32_t wk_free(wk_queue *q, void *dptr);                   /* cl.buffer.release, main.zig:258 */

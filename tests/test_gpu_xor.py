@@ -103,3 +103,48 @@ def test_cpp_host_mirror_xor_example_matches_python_path(oracle):
     opt.deinit(pipe)
     cache.deinit(pipe)
     seq.deinit(pipe)
+
+
+def test_training_step_as_cuda_graph_matches_eager(oracle):
+    """one XOR training step (forward + mse + backward + GD, ~22 launches) captured once and replayed as a CUDA graph
+    leaves the same weights, bit for bit, as launching every op eagerly"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    steps = 60
+
+    def make():
+        inputs, expected, seq, layers, cache, opt = _build(wk, ctx, pipe, np.float32, (42, 43), False)
+        layer_cache = cache.get_layer_cache(0)
+
+        def step():
+            output = layers.forward(pipe, inputs, layer_cache)
+            wk.nn.mse(pipe, output, expected, cache, calculate_derivative=True)
+            layers.backward(pipe, layer_cache, inputs, None)
+            opt.step(pipe, cache)
+        return step, seq, cache, opt
+
+    step_a, seq_a, cache_a, opt_a = make()
+    for _ in range(steps):
+        step_a()
+    want = [gh.to_np(l.weights[0]) for l in seq_a.layers] + [gh.to_np(l.bias[0]) for l in seq_a.layers]
+
+    step_b, seq_b, cache_b, opt_b = make()
+    step_b()  # eager warm-up (first-call attribute setup happens outside the capture)
+    pipe.wait_and_cleanup()
+    pipe.begin_capture()
+    step_b()
+    graph = pipe.end_capture()
+    assert graph.num_kernels >= 15
+    launches0 = wk.capi.launch_count()
+    for _ in range(steps - 1):
+        graph.launch(pipe)
+    pipe.wait_and_cleanup()
+    assert wk.capi.launch_count() - launches0 == (steps - 1) * graph.num_kernels
+    got = [gh.to_np(l.weights[0]) for l in seq_b.layers] + [gh.to_np(l.bias[0]) for l in seq_b.layers]
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    graph.release()
+    for opt, cache, seq in ((opt_a, cache_a, seq_a), (opt_b, cache_b, seq_b)):
+        opt.deinit(pipe)
+        cache.deinit(pipe)
+        seq.deinit(pipe)

@@ -85,6 +85,11 @@ SIGNATURES = {
     "wk_event_wait": [_vp],
     "wk_event_elapsed_ms": [_vp, _vp, C.POINTER(C.c_float)],
     "wk_event_release": [_vp],
+    "wk_graph_begin_capture": [_vp],
+    "wk_graph_end_capture": [_vp, _pp],
+    "wk_graph_launch": [_vp, _vp],
+    "wk_graph_num_kernels": [_vp, C.POINTER(C.c_uint64)],
+    "wk_graph_release": [_vp],
     "wk_malloc": [_vp, _sz, _pp],
     "wk_free": [_vp, _vp],
     "wk_host_alloc": [_sz, _pp],

@@ -175,6 +175,15 @@ class Pipeline:
         wait-list argument of clEnqueue* (pipeline.prevEvents), for copy / compute overlap across queues"""
         capi.check(capi.lib().wk_queue_wait_event(self.q, event))
 
+    def begin_capture(self) -> None:
+        """record, instead of executing, everything enqueued on this pipeline until end_capture()"""
+        capi.check(capi.lib().wk_graph_begin_capture(self.q))
+
+    def end_capture(self) -> "Graph":
+        g = C.c_void_p()
+        capi.check(capi.lib().wk_graph_end_capture(self.q, C.byref(g)))
+        return Graph(g)
+
     def wait_and_cleanup(self) -> None:
         capi.check(capi.lib().wk_queue_finish(self.q))
         self.clear()
@@ -186,3 +195,21 @@ class Pipeline:
 
     def deinit(self) -> None:
         self.wait_and_cleanup()
+
+
+class Graph:
+    """a captured op sequence (CUDA graph): `launch(pipeline)` replays it as one launch"""
+
+    def __init__(self, handle):
+        self._h = handle
+        n = C.c_uint64()
+        capi.check(capi.lib().wk_graph_num_kernels(self._h, C.byref(n)))
+        self.num_kernels = int(n.value)
+
+    def launch(self, pipeline: Pipeline) -> None:
+        capi.check(capi.lib().wk_graph_launch(self._h, pipeline.q))
+
+    def release(self) -> None:
+        if self._h is not None:
+            capi.lib().wk_graph_release(self._h)
+            self._h = None

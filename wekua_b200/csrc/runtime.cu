@@ -270,6 +270,74 @@ WK_API int32_t wk_event_release(wk_event *ev) {
     return WK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ graphs
+// A training step of a small network is ~25 launches of microsecond kernels: launch-bound.  The ops
+// enqueued between begin and end are captured instead of executed and replay as ONE graph launch.  Blocking entries
+// (wk_sum, wk_get_value, wk_dot_reduce, wk_free) must not be called while capturing.
+struct wk_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int device = 0;
+    uint64_t kernel_nodes = 0;
+};
+
+WK_API int32_t wk_graph_begin_capture(wk_queue *q) {
+    WK_CHECK_QUEUE(q);
+    WK_CUDA(cudaStreamBeginCapture(q->stream, cudaStreamCaptureModeRelaxed));
+    return WK_OK;
+}
+
+WK_API int32_t wk_graph_end_capture(wk_queue *q, wk_graph **out) {
+    WK_CHECK_QUEUE(q);
+    if (!out) return WK_ERR_INVALID_VALUE;
+    *out = nullptr;
+    wk_graph *g = new (std::nothrow) wk_graph();
+    if (!g) return WK_ERR_OUT_OF_MEMORY;
+    g->device = q->device;
+    cudaError_t e = cudaStreamEndCapture(q->stream, &g->graph);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+        return cuda_fail(e, "graph capture / instantiate", __FILE__, __LINE__);
+    }
+    size_t n = 0;
+    if (cudaGraphGetNodes(g->graph, nullptr, &n) == cudaSuccess && n > 0) {
+        cudaGraphNode_t *nodes = new (std::nothrow) cudaGraphNode_t[n];
+        if (nodes && cudaGraphGetNodes(g->graph, nodes, &n) == cudaSuccess)
+            for (size_t i = 0; i < n; i++) {
+                cudaGraphNodeType t;
+                if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernel_nodes++;
+            }
+        delete[] nodes;
+    }
+    *out = g;
+    return WK_OK;
+}
+
+WK_API int32_t wk_graph_launch(wk_graph *g, wk_queue *q) {
+    WK_CHECK_QUEUE(q);
+    if (!g || !g->exec) return WK_ERR_INVALID_VALUE;
+    WK_CUDA(cudaGraphLaunch(g->exec, q->stream));
+    count_launch(g->kernel_nodes);
+    return WK_OK;
+}
+
+WK_API int32_t wk_graph_num_kernels(const wk_graph *g, uint64_t *n) {
+    if (!g || !n) return WK_ERR_INVALID_VALUE;
+    *n = g->kernel_nodes;
+    return WK_OK;
+}
+
+WK_API int32_t wk_graph_release(wk_graph *g) {
+    if (!g) return WK_OK;
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return WK_OK;
+}
+
 // ------------------------------------------------------------------------------------------ memory
 WK_API int32_t wk_malloc(wk_queue *q, size_t bytes, void **dptr) {
     WK_CHECK_QUEUE(q);
