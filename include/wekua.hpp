@@ -7,6 +7,7 @@
 // wekua::Error carrying the TensorErrors member name (src/tensor/main.zig:25-33).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -286,11 +287,19 @@ template <typename T> void identity(Pipeline *p, Tensor<T> *t) {  // identity.zi
     check(wk_identity(p->q(), Tensor<T>::type_index, t->buffer, t->number_of_elements, t->shape[0], t->pitchSum()));
 }
 template <typename T> void transpose(Pipeline *p, Tensor<T> *result, const Tensor<T> *t, size_t dim0, size_t dim1) {  // transpose.zig:15-113
-    if (result->shape.size() != t->shape.size()) fail(WK_ERR_UNEQUAL_DIMENSION);
-    if (t->shape.size() != 2 || dim0 > 1 || dim1 > 1) fail(WK_ERR_INVALID_VALUE);
+    const size_t nd = t->shape.size();
+    if (result->shape.size() != nd) fail(WK_ERR_UNEQUAL_DIMENSION);
+    if (dim0 >= nd || dim1 >= nd) fail(WK_ERR_INVALID_VALUE);
+    if (t->number_of_elements_without_padding != result->number_of_elements_without_padding) fail(WK_ERR_UNEQUAL_DIMENSION);
+    if (result->shape[dim0] != t->shape[dim1] || result->shape[dim1] != t->shape[dim0]) fail(WK_ERR_INVALID_VALUE);
     if (dim0 == dim1) return memory::copy(p, t, result);
-    if (result->shape[0] != t->shape[1] || result->shape[1] != t->shape[0]) fail(WK_ERR_INVALID_VALUE);
-    check(wk_transpose2d(p->q(), Tensor<T>::type_index, t->rows, t->cols, t->buffer, t->row_pitch, result->buffer, result->row_pitch));
+    if (nd == 2) {
+        check(wk_transpose2d(p->q(), Tensor<T>::type_index, t->rows, t->cols, t->buffer, t->row_pitch, result->buffer, result->row_pitch));
+        return;
+    }
+    check(wk_transpose_nd(p->q(), Tensor<T>::type_index, (uint32_t)nd, t->buffer, t->pitches.data(), result->buffer, result->pitches.data(),
+                          t->row_pitch, t->slice_pitch, t->rows * t->row_pitch, t->cols, t->number_of_elements,
+                          (uint32_t)std::min(dim0, dim1), (uint32_t)std::max(dim0, dim1)));
 }
 namespace random {
 // random.uniform(T, pipeline, tensor, ?seed, ?min, ?max), uniform.zig:60-123; seed == nullopt -> time() like :82

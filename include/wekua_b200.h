@@ -214,6 +214,13 @@ int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, ui
 int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_t cols, const void *src, uint64_t src_pitch,
                        void *dst, uint64_t dst_pitch);
 
+/* transpose (src/tensor/transpose.zig:15-113 + transpose.cl:3-42), any rank <= 8: swaps dim0 and dim1 through the two
+ * tensors' pitch arrays.  row_pitch / slice_pitch / cols of the SOURCE, height = rows * row_pitch, n_elements = the
+ * source's padded element count -- exactly the arguments transpose.zig:68-86 sets. */
+int32_t wk_transpose_nd(wk_queue *q, int32_t dtype, uint32_t ndim, const void *src, const uint64_t *src_pitches, void *dst,
+                        const uint64_t *dst_pitches, uint64_t row_pitch, uint64_t slice_pitch, uint64_t height, uint64_t cols,
+                        uint64_t n_elements, uint32_t dim0, uint32_t dim1);
+
 /* --------------------------------------------------------------------------------------- multi-GPU */
 /* Row-sharded GEMM with the all-gather of C fused into the epilogue (new; the reference's multi-device
  * mode is "one queue per device", src/core/command_queue.zig:160-181).  This rank computes rows

@@ -291,6 +291,22 @@ def test_fill_identity_transpose_uniform_vs_oracle(oracle, dtype):
     wk.tensor.transpose(pipe, dst, src, 0, 1)
     oracle.transpose(odst, osrc, 0, 1)
     np.testing.assert_array_equal(gh.padded(dst), odst.buf)
+    # N-D: every pair of dimensions of a ragged 3-D and a 4-D tensor (transpose.zig tests + transpose.cl:3-42)
+    for shape in [(2, 3, 4), (3, 5, 7), (2, 3, 5, 6)]:
+        nd = len(shape)
+        n = int(np.prod(shape))
+        for d0 in range(nd):
+            for d1 in range(d0 + 1, nd):
+                rshape = list(shape)
+                rshape[d0], rshape[d1] = rshape[d1], rshape[d0]
+                src, osrc = gh.make_pair(oracle, dtype, shape, (np.arange(n) % 120).reshape(shape))
+                dst, odst = gh.make_pair(oracle, dtype, tuple(rshape))
+                wk.tensor.transpose(pipe, dst, src, d1, d0)
+                oracle.transpose(odst, osrc, d0, d1)
+                np.testing.assert_array_equal(gh.padded(dst), odst.buf)
+                np.testing.assert_array_equal(gh.to_np(dst), np.swapaxes((np.arange(n) % 120).reshape(shape), d0, d1).astype(dtype))
+                for t in (src, dst):
+                    t.release(pipe)
     for shape in [(64, 100), (5, 7), (3, 5, 7), (1001,)]:
         for seed in (42, 43):
             t, o = gh.make_pair(oracle, dtype, shape)

@@ -124,6 +124,8 @@ SIGNATURES = {
     "wk_identity": [_vp, _i32, _vp, _u64, _u64, _u64],
     "wk_uniform": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _u64, _vp, _vp],
     "wk_transpose2d": [_vp, _i32, _u64, _u64, _vp, _u64, _vp, _u64],
+    "wk_transpose_nd": [_vp, _i32, C.c_uint32, _vp, C.POINTER(_u64), _vp, C.POINTER(_u64), _u64, _u64, _u64, _u64, _u64,
+                        C.c_uint32, C.c_uint32],
     "wk_gemm_rowshard_allgather": [_vp, _i32, _i32, _i32, _u64, _u64, _u64, _vp, _vp, _u64, _vp, _u64, _vp, _u64, _pp,
                                    _i32, _i32, _u64],
     "wk_ipc_get_handle": [_vp, _vp, _vp],

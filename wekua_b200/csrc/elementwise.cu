@@ -383,6 +383,27 @@ __global__ void __launch_bounds__(256) transpose2d_kernel(const T *__restrict__ 
     }
 }
 
+// N-D swap of two dimensions through the pitch arrays (transpose.cl:3-42): one thread per PADDED source element,
+// padding skipped, the destination index rebuilt dimension by dimension with dim0/dim1's pitches exchanged.
+struct TransposeNd {
+    uint64_t pa[8], pb[8];
+    uint64_t row_pitch, slice_pitch, height, cols, n;
+    uint32_t ndim, dim0, dim1;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_nd_kernel(const T *__restrict__ a, T *__restrict__ b, const TransposeNd p) {
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 256 + threadIdx.x; i0 < p.n; i0 += (uint64_t)gridDim.x * 256) {
+        if ((i0 % p.row_pitch) >= p.cols || (i0 % p.slice_pitch) >= p.height) continue;
+        uint64_t index = i0, b_index = 0;
+        for (uint32_t x = 0; x < p.ndim; x++) {
+            const uint64_t dim_index = index / p.pa[x];
+            index -= dim_index * p.pa[x];
+            b_index += dim_index * p.pb[x == p.dim0 ? p.dim1 : (x == p.dim1 ? p.dim0 : x)];
+        }
+        b[b_index + index] = a[i0];
+    }
+}
+
 // axpy.zig:66-91 isSubstracting
 template <typename T> static bool is_subtracting(const void *alpha) {
     if (std::is_unsigned<T>::value) return false;
@@ -585,6 +606,31 @@ WK_API int32_t wk_identity(wk_queue *q, int32_t dtype, void *buf, uint64_t n_tot
     return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
         WK_CUDA(cudaMemsetAsync(buf, 0, n_total * sizeof(scalar_t), q->stream));  // fill.zeroes, identity.zig:28
         identity_kernel<scalar_t><<<(unsigned)((size + 255) / 256), 256, 0, q->stream>>>((scalar_t *)buf, size, pitch_sum);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}
+
+WK_API int32_t wk_transpose_nd(wk_queue *q, int32_t dtype, uint32_t ndim, const void *src, const uint64_t *src_pitches, void *dst,
+                               const uint64_t *dst_pitches, uint64_t row_pitch, uint64_t slice_pitch, uint64_t height, uint64_t cols,
+                               uint64_t n_elements, uint32_t dim0, uint32_t dim1) {
+    WK_CHECK_QUEUE(q);
+    if (!src || !dst || !src_pitches || !dst_pitches) return WK_ERR_INVALID_BUFFER;
+    if (ndim == 0 || ndim > 8 || dim0 >= ndim || dim1 >= ndim || row_pitch == 0 || slice_pitch == 0) return WK_ERR_INVALID_VALUE;
+    if (n_elements == 0) return WK_OK;
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+        TransposeNd p{};
+        for (uint32_t i = 0; i < ndim; i++) {
+            if (src_pitches[i] == 0) return WK_ERR_INVALID_VALUE;
+            p.pa[i] = src_pitches[i];
+            p.pb[i] = dst_pitches[i];
+        }
+        p.row_pitch = row_pitch; p.slice_pitch = slice_pitch; p.height = height; p.cols = cols; p.n = n_elements;
+        p.ndim = ndim; p.dim0 = dim0; p.dim1 = dim1;
+        uint64_t blocks = (n_elements + 255) / 256;
+        const uint64_t cap = (uint64_t)q->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        transpose_nd_kernel<scalar_t><<<(unsigned)blocks, 256, 0, q->stream>>>((const scalar_t *)src, (scalar_t *)dst, p);
         WK_CHECK_LAUNCH();
         return WK_OK;
     });

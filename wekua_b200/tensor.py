@@ -238,7 +238,7 @@ def identity(pipeline: Pipeline, tensor: Tensor) -> None:
 
 
 def transpose(pipeline: Pipeline, result_tensor: Tensor, tensor: Tensor, dim0: int, dim1: int) -> None:
-    """transpose.zig:15-113 (2-D tensors; N-D permutations are out of scope for this round)"""
+    """transpose.zig:15-113: swap two dimensions (any rank; 2-D takes the shared-memory tiled kernel)"""
     if len(result_tensor.shape) != len(tensor.shape):
         raise capi.UnqualTensorsDimension("UnqualTensorsDimension")
     nd = len(tensor.shape)
@@ -252,7 +252,13 @@ def transpose(pipeline: Pipeline, result_tensor: Tensor, tensor: Tensor, dim0: i
         memory.copy(pipeline, tensor, result_tensor)
         return
     if nd != 2:
-        raise capi.InvalidValue("transpose: only 2-D tensors are implemented on the CUDA backend")
+        d0, d1 = min(dim0, dim1), max(dim0, dim1)
+        pa = (C.c_uint64 * nd)(*tensor.pitches)
+        pb = (C.c_uint64 * nd)(*result_tensor.pitches)
+        capi.check(capi.lib().wk_transpose_nd(pipeline.q, tensor.type_index, nd, tensor.ptr, pa, result_tensor.ptr, pb,
+                                              tensor.row_pitch, tensor.slice_pitch, tensor.rows * tensor.row_pitch, tensor.cols,
+                                              tensor.number_of_elements, d0, d1))
+        return
     capi.check(capi.lib().wk_transpose2d(pipeline.q, tensor.type_index, tensor.rows, tensor.cols, tensor.ptr,
                                          tensor.row_pitch, result_tensor.ptr, result_tensor.row_pitch))
 
