@@ -42,6 +42,9 @@ def measured_peaks():
 
 
 FP64_DMMA_PEAK_TFLOPS = 37.04  # profiles/mma_peak_fp64_r01.txt
+# tcgen05.mma kind::tf32, MMA-only loop (operands resident in smem, TMEM accumulators) on this pool's B200,
+# tools/mma_peak_tf32.cu -> profiles/mma_peak_tf32_r01.txt: 900.6-903.2 TF/s over ~3 s (power-capped clock), 1045 burst
+TF32_MMA_PEAK_TFLOPS = {"sustained": 903.2, "burst": 1044.9}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture of each kernel on B200
 NCU_TRAFFIC_BYTES = {
     "gemm_f32_n32768_1gpu": 167.3e9,  # profiles/ncu_gemm_f32_r01c_n32768.txt (algorithmic A+B+C = 12.9e9; the
@@ -214,16 +217,23 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------ our arm
 def gemm_roofline(tflops, dtype, peaks, sustained, traffic=None):
     bf16 = peaks["bf16_tflops_sustained" if sustained else "bf16_tflops"]
+    extra = {}
     if dtype == "f32":
-        peak = bf16 / 2.0 / 3.0
-        basis = (f"{peaks['_source']} cuBLAS bf16 {'sustained' if sustained else 'burst'} {bf16:.0f} TF/s / 2 (tf32 rate) / 3 "
-                 "(3xTF32 passes per useful flop)")
+        # MEASURED_PEAKS.json has no TF32 entry, and bf16/2/3 sits BELOW what this kernel reaches (frac > 1: at equal
+        # power TF32 MMAs clock higher than cuBLAS bf16), so the denominator is the tensor pipe itself, measured
+        which = "sustained" if sustained else "burst"
+        peak = TF32_MMA_PEAK_TFLOPS[which] / 3.0
+        basis = (f"tcgen05.mma kind::tf32 MMA-only loop {which} {TF32_MMA_PEAK_TFLOPS[which]:.0f} TF/s measured on this pool's "
+                 "B200 (tools/mma_peak_tf32.cu, profiles/mma_peak_tf32_r01.txt) / 3 (3xTF32 passes per useful flop); "
+                 "MEASURED_PEAKS.json has no TF32 entry")
+        extra = {"peak_from_bf16": bf16 / 6.0, "frac_of_bf16_derived": tflops / (bf16 / 6.0),
+                 "bf16_basis": f"{peaks['_source']} cuBLAS bf16 {which} {bf16:.0f} TF/s / 2 / 3"}
     else:
         peak = FP64_DMMA_PEAK_TFLOPS
         basis = ("DMMA m16n8k16 register-only loop measured on this pool's B200 by tools/mma_peak.cu "
                  "(profiles/mma_peak_fp64_r01.txt; MEASURED_PEAKS.json has no FP64 entry; spec 40 TF/s)")
     return {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
-            "traffic": traffic, "peak_basis": basis}
+            "traffic": traffic, "peak_basis": basis, **extra}
 
 
 def hbm_roofline(gbs, peaks, traffic=None):
