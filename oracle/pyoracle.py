@@ -15,18 +15,60 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 MAX_DIMS = 8
-NP_DTYPES = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64]
+REAL_DTYPES = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64]
+
+
+def cx(base) -> np.dtype:
+    """Complex(T) of src/core/types.zig:6-11 as a numpy structured dtype {re, im} (numpy has no complex integers)"""
+    return np.dtype([("re", np.dtype(base)), ("im", np.dtype(base))])
+
+
+CX_DTYPES = [cx(d) for d in REAL_DTYPES]
+NP_DTYPES = REAL_DTYPES + CX_DTYPES  # index = getTypeIndex, types.zig:60-87
 DTYPE_NAMES = ["i8", "u8", "i16", "u16", "i32", "u32", "i64", "u64", "f32", "f64"]
+DTYPE_NAMES += ["c" + n for n in DTYPE_NAMES]
 NO_TRANSPOSE, TRANSPOSE = 0, 1
 UNARY_OPS = {"sin": 0, "cos": 1, "tan": 2, "sinh": 3, "cosh": 4, "tanh": 5, "sigmoid": 6}
 
 
 def dtype_id(dt) -> int:
     dt = np.dtype(dt)
+    if dt == np.complex64:
+        return 18
+    if dt == np.complex128:
+        return 19
     for i, d in enumerate(NP_DTYPES):
         if np.dtype(d) == dt:
             return i
     raise TypeError(f"unsupported dtype {dt}")
+
+
+def is_complex(dt) -> bool:
+    return dtype_id(dt) >= 10
+
+
+def as_dtype(values, dt) -> np.ndarray:
+    """host values -> contiguous array of element type dt; for Complex(T): real input becomes {v, 0}, python /
+    numpy complex input becomes {re, im}, (..., 2)-shaped pairs are NOT guessed (build them with cx_pairs)"""
+    dt = NP_DTYPES[dtype_id(dt)]
+    dt = np.dtype(dt)
+    a = np.asarray(values)
+    if dt.names is None:
+        return np.ascontiguousarray(a, dtype=dt)
+    if a.dtype == dt:
+        return np.ascontiguousarray(a)
+    out = np.zeros(a.shape, dtype=dt)
+    if a.dtype.kind == "c":
+        out["re"], out["im"] = a.real, a.imag
+    else:
+        out["re"] = a
+    return out
+
+
+def cx_pairs(re, im, base) -> np.ndarray:
+    out = np.zeros(np.shape(re), dtype=cx(base))
+    out["re"], out["im"] = re, im
+    return out
 
 
 class Device(C.Structure):
@@ -187,6 +229,11 @@ def _ptr(a):
 def _scalar(dt, v):
     if v is None:
         return None
+    dt = np.dtype(dt)
+    if dt.names is not None:
+        if isinstance(v, tuple):
+            return cx_pairs([v[0]], [v[1]], dt["re"])
+        return as_dtype(np.array([v]), dt)
     return np.array([v]).astype(dt)
 
 
@@ -196,8 +243,9 @@ class OTensor:
 
     def __init__(self, dev: Device, dtype, shape, vectors_enabled: bool = True, fast: bool = False):
         self.dev = dev
-        self.np_dtype = np.dtype(dtype)
         self.dtype = dtype_id(dtype)
+        self.np_dtype = np.dtype(NP_DTYPES[self.dtype])
+        self.base_dtype = np.dtype(REAL_DTYPES[self.dtype % 10])
         self.layout = Layout()
         self._lib = lib(fast)
         shp = (C.c_uint64 * len(shape))(*shape)
@@ -209,7 +257,7 @@ class OTensor:
 
     # memory.readFromBuffer / writeToBuffer
     def read_from(self, host):
-        host = np.ascontiguousarray(host, dtype=self.np_dtype).reshape(-1)
+        host = as_dtype(host, self.np_dtype).reshape(-1)
         if host.size != self.layout.number_of_elements_without_padding:
             raise ValueError("InvalidBuffer")
         self._lib.wko_read_from_buffer(self.dtype, _ptr(self.buf), C.byref(self.layout), _ptr(host))
@@ -231,7 +279,7 @@ class OTensor:
         return self
 
     def uniform(self, seed, lo=None, hi=None):
-        a, b = _scalar(self.np_dtype, lo), _scalar(self.np_dtype, hi)
+        a, b = _scalar(self.base_dtype, lo), _scalar(self.base_dtype, hi)  # bounds are scalars of the base type
         self._lib.wko_uniform(self.dtype, _ptr(self.buf), C.byref(self.layout), seed, _ptr(a), _ptr(b))
         return self
 

@@ -18,6 +18,7 @@
 #define CAT(a, b, c) CAT_(a, b, c)
 #define NAME(x) CAT(x, SUF, VW)
 
+#define IS_COMPLEX 0
 /* integers: lanes computed in uint64_t (wrap-around), truncated on store */
 #ifndef WKO_FLOAT_ONLY
 #define IS_FLOAT 0
@@ -107,6 +108,125 @@
 #undef SUF
 #undef IS_FLOAT
 
+#undef FN_SIN
+#undef FN_COS
+#undef FN_TAN
+#undef FN_SINH
+#undef FN_COSH
+#undef FN_TANH
+#undef FN_EXP
+#undef FN_SQRT
+#undef IS_COMPLEX
+/* complex types (ids 10-19, src/core/types.zig:74-83): struct { BT re, im; }, vector width always 1 */
+#define IS_COMPLEX 1
+#define VW 1
+#ifndef WKO_FLOAT_ONLY
+#define IS_FLOAT 0
+#define ACC uint64_t
+#define CX_INT(BTYPE, SUFFIX)                        \
+    typedef struct { BTYPE re, im; } cx_##SUFFIX;
+CX_INT(int8_t, i8) CX_INT(uint8_t, u8) CX_INT(int16_t, i16) CX_INT(uint16_t, u16)
+CX_INT(int32_t, i32) CX_INT(uint32_t, u32) CX_INT(int64_t, i64) CX_INT(uint64_t, u64)
+#define T cx_i8
+#define BT int8_t
+#define SUF ci8
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_u8
+#define BT uint8_t
+#define SUF cu8
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_i16
+#define BT int16_t
+#define SUF ci16
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_u16
+#define BT uint16_t
+#define SUF cu16
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_i32
+#define BT int32_t
+#define SUF ci32
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_u32
+#define BT uint32_t
+#define SUF cu32
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_i64
+#define BT int64_t
+#define SUF ci64
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#define T cx_u64
+#define BT uint64_t
+#define SUF cu64
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef SUF
+#undef ACC
+#undef IS_FLOAT
+#endif /* WKO_FLOAT_ONLY */
+#define IS_FLOAT 1
+typedef struct { float re, im; } cx_f32;
+typedef struct { double re, im; } cx_f64;
+#define T cx_f32
+#define BT float
+#define ACC float
+#define SUF cf32
+#define FN_SIN sinf
+#define FN_COS cosf
+#define FN_SINH sinhf
+#define FN_COSH coshf
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef ACC
+#undef SUF
+#undef FN_SIN
+#undef FN_COS
+#undef FN_SINH
+#undef FN_COSH
+#define T cx_f64
+#define BT double
+#define ACC double
+#define SUF cf64
+#define FN_SIN sin
+#define FN_COS cos
+#define FN_SINH sinh
+#define FN_COSH cosh
+#include "kernels.inc"
+#undef T
+#undef BT
+#undef ACC
+#undef SUF
+#undef FN_SIN
+#undef FN_COS
+#undef FN_SINH
+#undef FN_COSH
+#undef IS_FLOAT
+#undef IS_COMPLEX
+#undef VW
+
 #define LOAD_INT(p) load_int_scalar(dtype, p)
 #define LOAD_F32(p) (*(const float *)(p))
 #define LOAD_F64(p) (*(const double *)(p))
@@ -120,8 +240,22 @@
     X(6, i64, int64_t, uint64_t, LOAD_INT) X(7, u64, uint64_t, uint64_t, LOAD_INT)
 #endif
 #define ALL_TYPES(X) INT_TYPES(X) X(8, f32, float, float, LOAD_F32) X(9, f64, double, double, LOAD_F64)
+/* complex: X(id, suffix, storage struct, base type, lane type) */
+#ifdef WKO_FLOAT_ONLY
+#define CX_INT_TYPES(X)
+#else
+#define CX_INT_TYPES(X)                                                                              \
+    X(10, ci8, cx_i8, int8_t, uint64_t) X(11, cu8, cx_u8, uint8_t, uint64_t)                         \
+    X(12, ci16, cx_i16, int16_t, uint64_t) X(13, cu16, cx_u16, uint16_t, uint64_t)                   \
+    X(14, ci32, cx_i32, int32_t, uint64_t) X(15, cu32, cx_u32, uint32_t, uint64_t)                   \
+    X(16, ci64, cx_i64, int64_t, uint64_t) X(17, cu64, cx_u64, uint64_t, uint64_t)
+#endif
+#define CX_TYPES(X) CX_INT_TYPES(X) X(18, cf32, cx_f32, float, float) X(19, cf64, cx_f64, double, double)
 
-static const uint64_t DTYPE_SIZE[10] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 8};
+static const uint64_t DTYPE_SIZE[20] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 8, 2, 2, 4, 4, 8, 8, 16, 16, 8, 16};
+#define IS_CX(d) ((d) >= 10)
+/* load a complex scalar {re, im} of storage type TT into lanes of type ACCT */
+#define CX_LOAD(vecT, TT, ACCT, p) ((vecT){(ACCT)((const TT *)(p))->re, (ACCT)((const TT *)(p))->im})
 
 /* dispatch over dtype (d) and vector width (vw in {1,2,4,8,16}) */
 #define DISPATCH_VW(fn, suf, vw, ...)               \
@@ -199,7 +333,7 @@ static int32_t init_gemm_algorithm(const wko_device *dev, int32_t dtype, uint64_
     for (uint64_t bl = 2; bl < 128; bl *= 2)
         if (gwi_h % bl == 0 && gwi_w % bl == 0) max_block_length = bl;
     /* NB: the reference keeps the LAST dividing block length (:134-138), not the largest contiguous run */
-    const uint64_t vw = dev->vector_widths[dtype];
+    const uint64_t vw = IS_CX(dtype) ? 1 : dev->vector_widths[dtype]; /* work_configuration.zig:145-151 */
     int32_t algorithm = 0, idx = 0;
     for (uint64_t bl = 2; bl < 128; bl *= 2, idx++) {
         const uint64_t block_size = vw * bl * DTYPE_SIZE[dtype];
@@ -220,7 +354,7 @@ static int32_t init_gemm_algorithm(const wko_device *dev, int32_t dtype, uint64_
 /* ------------------------------------------------------------------ tensor/main.zig:113-251 */
 int32_t wko_layout_init(wko_layout *l, const wko_device *dev, int32_t dtype, const uint64_t *shape, uint64_t ndim,
                         int32_t vectors_enabled_cfg) {
-    if (ndim == 0 || ndim > WKO_MAX_DIMS || dtype < 0 || dtype > 9) return -1;
+    if (ndim == 0 || ndim > WKO_MAX_DIMS || dtype < 0 || dtype > 19) return -1;
     memset(l, 0, sizeof(*l));
     l->ndim = ndim;
     for (uint64_t i = 0; i < ndim; i++) {
@@ -228,7 +362,7 @@ int32_t wko_layout_init(wko_layout *l, const wko_device *dev, int32_t dtype, con
         l->shape[i] = shape[i];
         l->vl_shape[i] = shape[i];
     }
-    int vectors_enabled = vectors_enabled_cfg != 0;
+    int vectors_enabled = !IS_CX(dtype) && vectors_enabled_cfg != 0; /* main.zig:142 `!is_complex and config.vectors_enabled` */
     uint64_t vw = 1;
     if (vectors_enabled) {
         if (dev->vector_widths[dtype] > vw) vw = dev->vector_widths[dtype];
@@ -290,7 +424,8 @@ int32_t wko_get_algorithm(int32_t default_algorithm, uint64_t k_size) {
 /* ------------------------------------------------------------------ gemm.zig:117-186 */
 int32_t wko_packed_init(wko_packed_geom *g, const wko_device *dev, int32_t dtype, uint64_t n_size, uint64_t m_size,
                         uint64_t k_size, int32_t default_algorithm, int32_t vectors_enabled) {
-    const uint64_t vw = dev->vector_widths[dtype];
+    if (IS_CX(dtype)) vectors_enabled = 0; /* gemm.zig:129,150,181 `!is_complex and vectors_enabled` */
+    const uint64_t vw = IS_CX(dtype) ? 1 : dev->vector_widths[dtype];
     uint64_t padded_k = k_size;
     if (vectors_enabled) {
         const uint64_t rem = padded_k % (vw * 2);
@@ -345,6 +480,15 @@ int32_t wko_pack(const wko_packed_geom *g, int32_t dtype, const void *a, const w
 #define X(id, suf, TT, ACCT, LOADS) case id: PACK_CASE(suf, TT)
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT)                                                                                 \
+    case id:                                                                                                      \
+        pack_##suf##_v1((const TT *)a, (TT *)pa, la->row_pitch, g->a.slice_pitch, g->a.row_pitch, la->shape[0],   \
+                        la->shape[1], a_transpose, bs, g->a.shape[0], g->a.shape[1], g->a.shape[2]);              \
+        pack_##suf##_v1((const TT *)b, (TT *)pb, lb->row_pitch, g->b.slice_pitch, g->b.row_pitch, lb->shape[0],   \
+                        lb->shape[1], b_transpose, bs, g->b.shape[0], g->b.shape[1], g->b.shape[2]);              \
+        break;
+        CX_TYPES(X)
+#undef X
         default: return -1;
     }
     return 0;
@@ -395,13 +539,50 @@ static int validate_gemm(const wko_layout *la, const wko_layout *lb, const wko_l
     }                                                                                                             \
     break;
 
+/* complex: alpha defaults to {1, 0} when only beta is given (gemm.zig:592-596) */
+#define CX_SCALARS(suf, TT, ACCT)                                                                                 \
+    const vec_##suf##_v1 al = has_alpha ? (alpha ? CX_LOAD(vec_##suf##_v1, TT, ACCT, alpha)                       \
+                                                 : (vec_##suf##_v1){(ACCT)1, (ACCT)0})                             \
+                                        : (vec_##suf##_v1){(ACCT)0, (ACCT)0};                                      \
+    const vec_##suf##_v1 be = has_beta ? CX_LOAD(vec_##suf##_v1, TT, ACCT, beta) : (vec_##suf##_v1){(ACCT)0, (ACCT)0};
+
+#define GEMM_UNPACKED_CX_CASE(suf, TT, ACCT)                                                                      \
+    {                                                                                                             \
+        CX_SCALARS(suf, TT, ACCT)                                                                                 \
+        if (dev->local_mem_type == WKO_MEM_LOCAL)                                                                 \
+            gemm_nxn_gpu_##suf##_v1((const TT *)a, (const TT *)b, (TT *)c, a_rp, b_rp, lc->row_pitch, k_size,     \
+                                    op_a, op_b, has_alpha, has_beta, al, be, gh / 2, gw / 2, bs);                 \
+        else if (algo == 0)                                                                                       \
+            gemm_2x2_##suf##_v1((const TT *)a, (const TT *)b, (TT *)c, a_rp, b_rp, lc->row_pitch, k_size, op_a,   \
+                                op_b, has_alpha, has_beta, al, be, gh / 2, gw / 2);                               \
+        else                                                                                                      \
+            gemm_nxn_##suf##_v1((const TT *)a, (const TT *)b, (TT *)c, a_rp, b_rp, lc->row_pitch, k_size, op_a,   \
+                                op_b, has_alpha, has_beta, al, be, gh / bs, gw / bs, bs);                         \
+    }                                                                                                             \
+    break;
+
+#define GEMM_PACKED_CX_CASE(suf, TT, ACCT)                                                                        \
+    {                                                                                                             \
+        CX_SCALARS(suf, TT, ACCT)                                                                                 \
+        if (dev->local_mem_type == WKO_MEM_LOCAL)                                                                 \
+            gemm_nxn_pack_gpu_##suf##_v1((const TT *)pa, (const TT *)pb, (TT *)c, A_sp, A_rp, B_sp, B_rp,         \
+                                         lc->row_pitch, cols, has_alpha, has_beta, al, be, gh / 2, gw / 2, bs);   \
+        else if (algo == 0)                                                                                       \
+            gemm_2x2_pack_##suf##_v1((const TT *)pa, (const TT *)pb, (TT *)c, A_sp, A_rp, B_sp, B_rp,             \
+                                     lc->row_pitch, cols, has_alpha, has_beta, al, be, gh / 2, gw / 2);           \
+        else                                                                                                      \
+            gemm_nxn_pack_##suf##_v1((const TT *)pa, (const TT *)pb, (TT *)c, A_sp, A_rp, B_sp, B_rp,             \
+                                     lc->row_pitch, cols, has_alpha, has_beta, al, be, gh / bs, gw / bs, bs);     \
+    }                                                                                                             \
+    break;
+
 static int32_t gemm_without_packing(const wko_device *dev, int32_t dtype, const void *alpha, const void *a,
                                     const wko_layout *la, int32_t op_a, const void *b, const wko_layout *lb,
                                     int32_t op_b, const void *beta, void *c, const wko_layout *lc) {
     /* gemm.zig:487-617 */
     const int has_alpha = (alpha != NULL || beta != NULL), has_beta = (beta != NULL);
     int vectors_enabled = la->vectors_enabled && lb->vectors_enabled;
-    if (dev->vector_widths[dtype] == 1) vectors_enabled = 0;
+    if (IS_CX(dtype) || dev->vector_widths[dtype] == 1) vectors_enabled = 0; /* gemm.zig:504 */
     else vectors_enabled &= (op_a == 0 && op_b == 1);
     uint64_t k_size;
     if (vectors_enabled) k_size = la->row_pitch_for_vectors;
@@ -416,6 +597,9 @@ static int32_t gemm_without_packing(const wko_device *dev, int32_t dtype, const 
     switch (dtype) {
 #define X(id, suf, TT, ACCT, LOADS) case id: GEMM_UNPACKED_CASE(suf, TT, ACCT, LOADS)
         ALL_TYPES(X)
+#undef X
+#define X(id, suf, TT, BTT, ACCT) case id: GEMM_UNPACKED_CX_CASE(suf, TT, ACCT)
+        CX_TYPES(X)
 #undef X
         default: return -1;
     }
@@ -449,6 +633,9 @@ static int32_t gemm_with_packing(const wko_device *dev, int32_t dtype, const voi
 #define X(id, suf, TT, ACCT, LOADS) case id: GEMM_PACKED_CASE(suf, TT, ACCT, LOADS)
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT) case id: GEMM_PACKED_CX_CASE(suf, TT, ACCT)
+        CX_TYPES(X)
+#undef X
         default: free(pa); free(pb); return -1;
     }
     free(pa);
@@ -481,6 +668,15 @@ static int is_subtracting(int32_t dtype, const void *alpha) {
         case 6: return *(const int64_t *)alpha == -1;
         case 8: return fabsf(*(const float *)alpha + 1.0f) < FLT_EPSILON;
         case 9: return fabs(*(const double *)alpha + 1.0) < DBL_EPSILON;
+        /* complex: alpha.real == -1 and alpha.imag in {0, -1} (axpy.zig:75-76,84 -- SURVEY Q3) */
+        case 10: { const int8_t *c = (const int8_t *)alpha; return c[0] == -1 && (c[1] == 0 || c[1] == -1); }
+        case 12: { const int16_t *c = (const int16_t *)alpha; return c[0] == -1 && (c[1] == 0 || c[1] == -1); }
+        case 14: { const int32_t *c = (const int32_t *)alpha; return c[0] == -1 && (c[1] == 0 || c[1] == -1); }
+        case 16: { const int64_t *c = (const int64_t *)alpha; return c[0] == -1 && (c[1] == 0 || c[1] == -1); }
+        case 18: { const float *c = (const float *)alpha;
+                   return fabsf(c[0] + 1.0f) < FLT_EPSILON && (fabsf(c[1]) < FLT_EPSILON || fabsf(c[1] + 1.0f) < FLT_EPSILON); }
+        case 19: { const double *c = (const double *)alpha;
+                   return fabs(c[0] + 1.0) < DBL_EPSILON && (fabs(c[1]) < DBL_EPSILON || fabs(c[1] + 1.0) < DBL_EPSILON); }
         default: return 0; /* unsigned */
     }
 }
@@ -507,6 +703,15 @@ int32_t wko_axpy(int32_t dtype, const void *x, const wko_layout *lx, const void 
 #define X(id, suf, TT, ACCT, LOADS) case id: AXPY_CASE(suf, TT, ACCT, LOADS)
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT)                                                                                 \
+    case id: {                                                                                                    \
+        const vec_##suf##_v1 al = mode == 1 ? CX_LOAD(vec_##suf##_v1, TT, ACCT, alpha) : (vec_##suf##_v1){(ACCT)0, (ACCT)0}; \
+        axpy_3d_##suf##_v1((const TT *)x, (TT *)y, lx->depth, lx->rows, lx->vl_shape[lx->ndim - 1],               \
+                           lx->slice_pitch_for_vectors, lx->row_pitch_for_vectors, ly->slice_pitch_for_vectors,   \
+                           ly->row_pitch_for_vectors, mode, al);                                                  \
+    } break;
+        CX_TYPES(X)
+#undef X
         default: return -1;
     }
     return 0;
@@ -530,6 +735,14 @@ int32_t wko_hadamard(int32_t dtype, void *x, const wko_layout *lx, const void *y
     switch (dtype) {
 #define X(id, suf, TT, ACCT, LOADS) case id: HAD_CASE(suf, TT)
         ALL_TYPES(X)
+#undef X
+#define X(id, suf, TT, BTT, ACCT)                                                                                 \
+    case id:                                                                                                      \
+        hadamard_3d_##suf##_v1((TT *)x, (const TT *)y, lx->depth, lx->rows, lx->vl_shape[lx->ndim - 1],           \
+                               lx->slice_pitch_for_vectors, lx->row_pitch_for_vectors,                            \
+                               ly->slice_pitch_for_vectors, ly->row_pitch_for_vectors);                           \
+        break;
+        CX_TYPES(X)
 #undef X
         default: return -1;
     }
@@ -566,6 +779,18 @@ int32_t wko_sum(const wko_device *dev, int32_t dtype, const void *x, const wko_l
 #define X(id, suf, TT, ACCT, LOADS) case id: SUM_CASE(suf, TT)
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT)                                                                                 \
+    case id: {                                                                                                    \
+        const TT *src = (const TT *)x;                                                                            \
+        if (last_dim > 1) {                                                                                       \
+            row_sum_##suf##_v1((const TT *)x, (TT *)tmp, lx->depth, lx->rows, lx->row_pitch_for_vectors,          \
+                               lx->slice_pitch_for_vectors, lx->rows);                                            \
+            src = (const TT *)tmp;                                                                                \
+        }                                                                                                         \
+        seq_sum_##suf##_v1(src, row_length, (TT *)out);                                                           \
+    } break;
+        CX_TYPES(X)
+#undef X
         default: free(tmp); return -1;
     }
     free(tmp);
@@ -587,6 +812,11 @@ int32_t wko_mean(const wko_device *dev, int32_t dtype, const void *x, const wko_
         case 7: *(uint64_t *)out = *(uint64_t *)out / n; break;
         case 8: *(float *)out = *(float *)out / (float)n; break;
         case 9: *(double *)out = *(double *)out / (double)n; break;
+        /* complex: each component on its own (basic.zig:216-227) */
+#define CXM(id, BTT) case id: { BTT *c = (BTT *)out; c[0] = (BTT)(c[0] / (BTT)n); c[1] = (BTT)(c[1] / (BTT)n); } break;
+        CXM(10, int8_t) CXM(11, uint8_t) CXM(12, int16_t) CXM(13, uint16_t) CXM(14, int32_t) CXM(15, uint32_t)
+        CXM(16, int64_t) CXM(17, uint64_t) CXM(18, float) CXM(19, double)
+#undef CXM
         default: return -1;
     }
     return 0;
@@ -600,6 +830,12 @@ int32_t wko_mean(const wko_device *dev, int32_t dtype, const void *x, const wko_
     return 0;
 
 int32_t wko_unary(int32_t dtype, void *x, uint64_t n, int32_t op) {
+    if (dtype == 18 || dtype == 19) { /* trig.cl complex branches; sigmoid's complex branch is not restated */
+        if (op < 0 || op > 5) return -3;
+        if (dtype == 18) unary_cf32_v1((cx_f32 *)x, n, op);
+        else unary_cf64_v1((cx_f64 *)x, n, op);
+        return 0;
+    }
     F_DISPATCH(unary_f32_v1((float *)x, n, op), unary_f64_v1((double *)x, n, op))
 }
 int32_t wko_sigmoid_dev(int32_t dtype, const void *o, void *d, uint64_t n) {
@@ -640,6 +876,10 @@ int32_t wko_fill(int32_t dtype, void *buf, const wko_layout *l, const void *scal
     case id: fill_##suf##_v1((TT *)buf, l->depth, l->rows, l->cols, l->row_pitch, l->slice_pitch, *(const TT *)scalar); break;
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT) \
+    case id: fill_##suf##_v1((TT *)buf, l->depth, l->rows, l->cols, l->row_pitch, l->slice_pitch, *(const TT *)scalar); break;
+        CX_TYPES(X)
+#undef X
         default: return -1;
     }
     return 0;
@@ -654,6 +894,10 @@ int32_t wko_identity(int32_t dtype, void *buf, const wko_layout *l) {
 #define X(id, suf, TT, ACCT, LOADS) \
     case id: identity_##suf##_v1((TT *)buf, l->pitches, l->ndim, size); break;
         ALL_TYPES(X)
+#undef X
+#define X(id, suf, TT, BTT, ACCT) \
+    case id: identity_##suf##_v1((TT *)buf, l->pitches, l->ndim, size); break;
+        CX_TYPES(X)
 #undef X
         default: return -1;
     }
@@ -678,6 +922,13 @@ int32_t wko_transpose(int32_t dtype, const void *a, const wko_layout *la, void *
         break;
         ALL_TYPES(X)
 #undef X
+#define X(id, suf, TT, BTT, ACCT)                                                                                   \
+    case id:                                                                                                        \
+        transpose_##suf##_v1((const TT *)a, la->pitches, (TT *)b, lb->pitches, la->row_pitch, la->slice_pitch, height, \
+                             width, d0, d1, la->ndim, la->number_of_elements);                                       \
+        break;
+        CX_TYPES(X)
+#undef X
         default: return -1;
     }
     return 0;
@@ -701,10 +952,17 @@ uint64_t wko_xxhash64(uint64_t index, uint64_t global_seed) {
 
 int32_t wko_uniform(int32_t dtype, void *buf, const wko_layout *l, uint64_t seed, const void *minp, const void *maxp) {
     const int range_defined = (minp != NULL || maxp != NULL);
+    const uint64_t ncomp = IS_CX(dtype) ? 2 : 1;
+    if (dtype < 0 || dtype > 19) return -1;
+    dtype %= 10; /* from here on: the base type; `index` addresses base-type scalars */
     for (uint64_t i = 0; i < l->depth; i++)
         for (uint64_t j = 0; j < l->rows; j++)
             for (uint64_t k = 0; k < l->cols; k++) {
-                const uint64_t index = i * l->slice_pitch + j * l->row_pitch + k;
+                const uint64_t eindex = i * l->slice_pitch + j * l->row_pitch + k;
+                /* complex: the two components hash (index << 1) and (index << 1) + 1 (uniform.cl:80-93) and are
+                 * stored next to each other; min/max/range are scalars of the base type (uniform.zig:64-65) */
+                for (uint64_t comp = 0; comp < ncomp; comp++) {
+                const uint64_t index = ncomp == 2 ? (eindex << 1) + comp : eindex;
                 const uint64_t h = wko_xxhash64(index, seed);
                 if (range_defined) {
                     /* uniform.cl:73-96 (cl_khr_fp64 branch): min + (double)h/ULONG_MAX * range, cast to T.
@@ -752,6 +1010,7 @@ int32_t wko_uniform(int32_t dtype, void *buf, const wko_layout *l, uint64_t seed
                         case 0: case 1: ((uint8_t *)buf)[index] = (uint8_t)(h & 0xFFu); break;
                         default: return -1;
                     }
+                }
                 }
             }
     return 0;

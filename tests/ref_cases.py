@@ -29,6 +29,25 @@ GEMM_PACKED = (
     + [("IB", 10, 6, N, T, True, None, None)]
 )
 
+# "gemm cpu - all algorithms, complex" (gemm.zig:1008-1052): data {i+1, 0}, alpha {2,0}, beta {3,0}; complex floats only
+GEMM_COMPLEX_CPU = (
+    [("AI", m, k, N, N, False, None, None) for m, k in [(6, 10), (5, 7), (12, 20), (24, 8), (16, 48), (32, 96), (64, 128)]]
+    + [("IB", m, n, N, N, False, None, None) for m, n in [(10, 6), (7, 5), (20, 12), (48, 16)]]
+    + [("AI", m, k, N, N, False, 2, None) for m, k in [(6, 10), (12, 20)]]
+    + [("AI", m, k, N, N, False, 2, 3) for m, k in [(6, 10), (12, 20)]]
+    + [("AI", m, k, T, N, False, None, None) for m, k in [(6, 10), (12, 20)]]
+    + [("IB", 10, 6, N, T, False, None, None)]
+)
+# "gemm gpu - all algorithms, complex" (gemm.zig:1188-1228): the same list without the alpha-only cases
+GEMM_COMPLEX_GPU = [c for c in GEMM_COMPLEX_CPU if not (c[6] is not None and c[7] is None)]
+# "gemm cpu|gpu - all algorithms with packing, complex" (gemm.zig:1096-1131, :1272-1307)
+GEMM_COMPLEX_PACKED = (
+    [("AI", m, k, N, N, True, None, None) for m, k in [(6, 10), (5, 7), (12, 20), (24, 8), (16, 48)]]
+    + [("IB", m, n, N, N, True, None, None) for m, n in [(10, 6), (20, 12)]]
+    + [("AI", m, k, N, N, True, 2, 3) for m, k in [(6, 10), (12, 20)]]
+    + [("AI", 6, 10, T, N, True, None, None), ("IB", 10, 6, N, T, True, None, None)]
+)
+
 # "gemm - invalid shapes" (gemm.zig:900-941): A[4,5] x B[6,7] -> C[4,7] must fail with InvalidValue
 GEMM_INVALID = [((4, 5), (6, 7), (4, 7), N, N)]
 
