@@ -10,21 +10,67 @@ import numpy as np
 
 from . import capi
 
-# src/core/types.zig:36-57 (real types; complex ids 10-19 are not in scope yet)
-SUPPORTED_TYPES = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32,
-                   np.float64]
+# src/core/types.zig:36-57 real types, then :74-83 Complex(T) of each of them (ids 10-19)
+REAL_TYPES = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64]
+
+
+def Complex(base) -> np.dtype:
+    """core.types.Complex(T) (types.zig:6-11): struct { real: T, imag: T } as a numpy structured dtype -- numpy has
+    complex64/128 only, the reference also has complex integers"""
+    return np.dtype([("re", np.dtype(base)), ("im", np.dtype(base))])
+
+
+SUPPORTED_TYPES = REAL_TYPES + [Complex(t) for t in REAL_TYPES]
+
+
+def is_complex(dtype) -> bool:
+    return get_type_index(dtype) >= 10
+
+
+def base_type(dtype) -> np.dtype:
+    return np.dtype(REAL_TYPES[get_type_index(dtype) % 10])
+
+
+def storage_dtype(dtype) -> np.dtype:
+    """the dtype host buffers of a tensor use: complex64/128 are accepted as names for Complex(f32/f64)"""
+    return np.dtype(SUPPORTED_TYPES[get_type_index(dtype)])
+
+
+def as_elements(values, dtype) -> np.ndarray:
+    """host values -> contiguous array of the tensor's element type.  Complex(T): real input becomes {v, 0} (the
+    reference tests' makeDataValue), python / numpy complex input {re, im}, (re, im) tuples for scalars"""
+    dt = storage_dtype(dtype)
+    if dt.names is None:
+        return np.ascontiguousarray(values, dtype=dt)
+    if isinstance(values, tuple) and len(values) == 2 and all(np.ndim(v) == 0 for v in values):
+        out = np.zeros((), dtype=dt)
+        out["re"], out["im"] = values
+        return out
+    a = np.asarray(values)
+    if a.dtype == dt:
+        return np.ascontiguousarray(a)
+    out = np.zeros(a.shape, dtype=dt)
+    if a.dtype.kind == "c":
+        out["re"], out["im"] = a.real, a.imag
+    else:
+        out["re"] = a
+    return out
 
 
 def get_type_index(dtype) -> int:
     """core.types.getTypeIndex (types.zig:60-87)"""
     dt = np.dtype(dtype)
+    if dt == np.complex64:
+        return 18
+    if dt == np.complex128:
+        return 19
     for i, t in enumerate(SUPPORTED_TYPES):
         if np.dtype(t) == dt:
             return i
     raise capi.TypeNotSupported(f"Type not supported: {dt}")
 
 
-get_type_id = get_type_index  # getTypeId == getTypeIndex for real types (types.zig:89-104)
+get_type_id = get_type_index  # getTypeId (types.zig:89-104)
 
 
 class CommandQueue:

@@ -200,7 +200,7 @@ struct AxpyF {
     __device__ __forceinline__ void operator()(T (&v)[2], uint64_t) const {
         using A = typename Acc<T>::type;
         const A x = to_acc<T>(v[0]), y = to_acc<T>(v[1]);
-        if (MODE == 1) v[1] = from_acc<T>((A)(y + alpha * x));
+        if (MODE == 1) v[1] = from_acc<T>((A)(y + x * alpha));  // complex: COMPLEX_MUL(x, alpha), axpy.cl:41-44
         else if (MODE == 2) v[1] = from_acc<T>((A)(y - x));
         else v[1] = from_acc<T>((A)(y + x));
     }
@@ -241,6 +241,21 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
         else if (OP == WK_OP_COSH) v[0] = cosh(x);
         else if (OP == WK_OP_TANH) v[0] = tanh(x);
         else v[0] = wk_sigmoid(x);
+    }
+};
+
+template <typename BT, int OP> struct UnaryF<Cx<BT>, OP> {  // trig.cl:5-66, complex branches
+    static constexpr unsigned kRead = 1, kWrite = 1;
+    __device__ __forceinline__ void operator()(Cx<BT> (&v)[1], uint64_t) const {
+        const BT a = v[0].re, b = v[0].im;
+        Cx<BT> r;
+        if (OP == WK_OP_SIN) { r.re = sin(a) * cosh(b); r.im = cos(a) * sinh(b); }
+        else if (OP == WK_OP_COS) { r.re = cos(a) * cosh(b); r.im = -sin(a) * sinh(b); }
+        else if (OP == WK_OP_TAN) { const BT ta = 2 * a, tb = 2 * b, d = cos(ta) + cosh(tb); r.re = sin(ta) / d; r.im = sinh(tb) / d; }
+        else if (OP == WK_OP_SINH) { r.re = sinh(a) * cos(b); r.im = cosh(a) * sin(b); }
+        else if (OP == WK_OP_COSH) { r.re = cosh(a) * cos(b); r.im = sinh(a) * sin(b); }
+        else { const BT ta = 2 * a, tb = 2 * b, d = cosh(ta) + cos(tb); r.re = sinh(ta) / d; r.im = sin(tb) / d; }
+        v[0] = r;
     }
 };
 
@@ -328,23 +343,35 @@ __device__ __forceinline__ uint64_t wk_xxhash64(uint64_t index, uint64_t seed) {
     return x2 ^ (x2 >> 28);
 }
 
+template <typename T, bool RANGE> __device__ __forceinline__ T uniform_value(uint64_t h, T min_value, T range) {
+    if (RANGE) {
+        // cl_khr_fp64 branch: (double)h / ULONG_MAX; ULONG_MAX converts to 2^64
+        const double normalized = (double)h / 18446744073709551616.0;
+        return (T)((double)min_value + normalized * (double)range);
+    } else if (std::is_same<T, float>::value) {
+        return (T)((float)h / 18446744073709551616.0f);
+    } else if (std::is_same<T, double>::value) {
+        return (T)((double)h / 18446744073709551616.0);
+    }
+    return (T)h;  // & WK_UINT_MAX == truncation
+}
+
 template <typename T, bool RANGE> struct UniformF {  // uniform.cl:56-185, idx = padded linear index
     static constexpr unsigned kRead = 0, kWrite = 1;
     uint64_t seed;
     T min_value, range;
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t idx) const {
-        const uint64_t h = wk_xxhash64(idx, seed);
-        if (RANGE) {
-            // cl_khr_fp64 branch: (double)h / ULONG_MAX; ULONG_MAX converts to 2^64
-            const double normalized = (double)h / 18446744073709551616.0;
-            v[0] = (T)((double)min_value + normalized * (double)range);
-        } else if (std::is_same<T, float>::value) {
-            v[0] = (T)((float)h / 18446744073709551616.0f);
-        } else if (std::is_same<T, double>::value) {
-            v[0] = (T)((double)h / 18446744073709551616.0);
-        } else {
-            v[0] = (T)h;  // & WK_UINT_MAX == truncation
-        }
+        v[0] = uniform_value<T, RANGE>(wk_xxhash64(idx, seed), min_value, range);
+    }
+};
+// complex branch, uniform.cl:80-93: the components hash (index << 1) and (index << 1) + 1; bounds are base-type scalars
+template <typename BT, bool RANGE> struct UniformF<Cx<BT>, RANGE> {
+    static constexpr unsigned kRead = 0, kWrite = 1;
+    uint64_t seed;
+    BT min_value, range;
+    __device__ __forceinline__ void operator()(Cx<BT> (&v)[1], uint64_t idx) const {
+        v[0].re = uniform_value<BT, RANGE>(wk_xxhash64(idx << 1, seed), min_value, range);
+        v[0].im = uniform_value<BT, RANGE>(wk_xxhash64((idx << 1) + 1, seed), min_value, range);
     }
 };
 
@@ -364,7 +391,7 @@ __global__ void __launch_bounds__(kThreads) bias_add_kernel(T *__restrict__ out,
 template <typename T>
 __global__ void identity_kernel(T *__restrict__ buf, uint64_t size, uint64_t pitch_sum) {  // identity.cl:3-20
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < size) buf[i * pitch_sum] = (T)1;
+    if (i < size) buf[i * pitch_sum] = Conv<T>::one();
 }
 
 template <typename T>
@@ -411,6 +438,20 @@ template <typename T> static bool is_subtracting(const void *alpha) {
     if (std::is_same<T, double>::value) return fabs(*(const double *)alpha + 1.0) < DBL_EPSILON;
     return *(const T *)alpha == (T)-1;
 }
+// complex: alpha.real == -1 and alpha.imag in {0, -1} (axpy.zig:75-76,84 -- the {-1,-1} case is the reference's quirk Q3)
+template <typename BT> static bool is_subtracting_cx(const void *alpha) {
+    if (std::is_unsigned<BT>::value) return false;
+    const BT *c = (const BT *)alpha;
+    if (std::is_same<BT, float>::value)
+        return fabsf((float)c[0] + 1.0f) < FLT_EPSILON && (fabsf((float)c[1]) < FLT_EPSILON || fabsf((float)c[1] + 1.0f) < FLT_EPSILON);
+    if (std::is_same<BT, double>::value)
+        return fabs((double)c[0] + 1.0) < DBL_EPSILON && (fabs((double)c[1]) < DBL_EPSILON || fabs((double)c[1] + 1.0) < DBL_EPSILON);
+    return c[0] == (BT)-1 && (c[1] == (BT)0 || c[1] == (BT)-1);
+}
+template <typename T> static bool is_sub(const void *alpha) {
+    if (IsCx<T>::value) return is_subtracting_cx<typename IsCx<T>::base>(alpha);
+    return is_subtracting<typename IsCx<T>::base>(alpha);
+}
 
 }  // namespace wk
 
@@ -419,11 +460,11 @@ using namespace wk;
 WK_API int32_t wk_axpy(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *alpha,
                        const void *x, uint64_t xrp, uint64_t xsp, void *y, uint64_t yrp, uint64_t ysp) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         Ptrs<2> p{{const_cast<void *>(x), y}};
         Pitches<2> pit{{xrp, yrp}, {xsp, ysp}};
-        if (!alpha) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 0>{0});
-        if (is_subtracting<scalar_t>(alpha)) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 2>{0});
+        if (!alpha) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 0>{acc_zero<scalar_t>()});
+        if (is_sub<scalar_t>(alpha)) return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 2>{acc_zero<scalar_t>()});
         return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, AxpyF<scalar_t, 1>{load_scalar<scalar_t>(alpha)});
     });
 }
@@ -432,7 +473,7 @@ WK_API int32_t wk_scal(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows
                        uint64_t xrp, uint64_t xsp) {
     WK_CHECK_QUEUE(q);
     if (!alpha) return WK_ERR_INVALID_VALUE;
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         Ptrs<1> p{{x}};
         Pitches<1> pit{{xrp}, {xsp}};
         return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, ScalF<scalar_t>{load_scalar<scalar_t>(alpha)});
@@ -442,7 +483,7 @@ WK_API int32_t wk_scal(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows
 WK_API int32_t wk_hadamard(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *x, uint64_t xrp,
                            uint64_t xsp, const void *y, uint64_t yrp, uint64_t ysp) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         Ptrs<2> p{{x, const_cast<void *>(y)}};
         Pitches<2> pit{{xrp, yrp}, {xsp, ysp}};
         return launch_map3d<scalar_t, 2>(q, p, pit, depth, rows, cols, HadamardF<scalar_t>{});
@@ -453,27 +494,28 @@ WK_API int32_t wk_fill(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows
                        uint64_t sp, const void *scalar) {
     WK_CHECK_QUEUE(q);
     if (!scalar) return WK_ERR_INVALID_VALUE;
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         Ptrs<1> p{{buf}};
         Pitches<1> pit{{rp}, {sp}};
-        return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, FillF<scalar_t>{*(const scalar_t *)scalar});
+        return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, FillF<scalar_t>{load_host<scalar_t>(scalar)});
     });
 }
 
 WK_API int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *buf, uint64_t rp,
                           uint64_t sp, uint64_t seed, const void *minp, const void *maxp) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
+        using base_t = typename IsCx<scalar_t>::base;  // min / max / range are scalars of the base type (uniform.zig:64-65)
         Ptrs<1> p{{buf}};
         Pitches<1> pit{{rp}, {sp}};
         // the hash is taken over the PADDED linear index (uniform.cl:73): the dense fast path is only valid when
         // padded index == dense index, which launch_map3d's density test guarantees.
         if (minp || maxp) {
             // uniform.zig:96-106: missing bound = type min / max (floats: -floatMax / floatMax); range = max - min in T
-            scalar_t mn = std::numeric_limits<scalar_t>::lowest(), mx = std::numeric_limits<scalar_t>::max();
-            if (minp) mn = *(const scalar_t *)minp;
-            if (maxp) mx = *(const scalar_t *)maxp;
-            const scalar_t range = (scalar_t)(mx - mn);
+            base_t mn = std::numeric_limits<base_t>::lowest(), mx = std::numeric_limits<base_t>::max();
+            if (minp) mn = *(const base_t *)minp;
+            if (maxp) mx = *(const base_t *)maxp;
+            const base_t range = (base_t)(mx - mn);
             return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, true>{seed, mn, range});
         }
         return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, false>{seed, 0, 0});
@@ -482,7 +524,11 @@ WK_API int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t r
 
 WK_API int32_t wk_unary(wk_queue *q, int32_t dtype, int32_t op, void *x, uint64_t n) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+    if (op == WK_OP_SIGMOID && dtype >= 10) {  // Sigmoid.run is f32/f64 only (sigmoid.zig:21-24 TypeNotSupported)
+        set_error("sigmoid: dtype %d not supported", dtype);
+        return WK_ERR_TYPE_NOT_SUPPORTED;
+    }
+    return WK_DISPATCH_FLOAT_CX(dtype, [&]() -> int32_t {
         Ptrs<1> p{{x}};
         switch (op) {
             case WK_OP_SIN: return launch_map<scalar_t, 1>(q, p, n, UnaryF<scalar_t, WK_OP_SIN>{});
@@ -603,7 +649,7 @@ WK_API int32_t wk_adam(wk_queue *q, int32_t dtype, void *x, const void *g, void 
 WK_API int32_t wk_identity(wk_queue *q, int32_t dtype, void *buf, uint64_t n_total, uint64_t size, uint64_t pitch_sum) {
     WK_CHECK_QUEUE(q);
     if (!buf) return WK_ERR_INVALID_BUFFER;
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         WK_CUDA(cudaMemsetAsync(buf, 0, n_total * sizeof(scalar_t), q->stream));  // fill.zeroes, identity.zig:28
         identity_kernel<scalar_t><<<(unsigned)((size + 255) / 256), 256, 0, q->stream>>>((scalar_t *)buf, size, pitch_sum);
         WK_CHECK_LAUNCH();
@@ -618,7 +664,7 @@ WK_API int32_t wk_transpose_nd(wk_queue *q, int32_t dtype, uint32_t ndim, const 
     if (!src || !dst || !src_pitches || !dst_pitches) return WK_ERR_INVALID_BUFFER;
     if (ndim == 0 || ndim > 8 || dim0 >= ndim || dim1 >= ndim || row_pitch == 0 || slice_pitch == 0) return WK_ERR_INVALID_VALUE;
     if (n_elements == 0) return WK_OK;
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_SIZE(dtype, [&]() -> int32_t {
         TransposeNd p{};
         for (uint32_t i = 0; i < ndim; i++) {
             if (src_pitches[i] == 0) return WK_ERR_INVALID_VALUE;
@@ -640,7 +686,7 @@ WK_API int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_
                               void *dst, uint64_t dp) {
     WK_CHECK_QUEUE(q);
     if (!src || !dst) return WK_ERR_INVALID_BUFFER;
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_SIZE(dtype, [&]() -> int32_t {
         dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
         if (grid.y > 65535) {
             set_error("transpose2d: too many rows");

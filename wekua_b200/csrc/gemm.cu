@@ -6,6 +6,7 @@
 // A float problem whose layout cannot feed the tensor-core loaders (pointer / pitch not 16-byte aligned) takes the
 // SIMT kernel as well.  There is no CPU path.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -58,6 +59,72 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
     }
     return gemm_simt(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
 }
+// Complex(T) GEMM (ids 10-19; the reference's complex branches: gemm_2x2.cl:121-236, gemm_nxn.cl:383-398) as ONE real
+// GEMM of shape M x 2N x 2K on the real back-ends -- derivation and operand layouts in complex.cu.
+//   alpha: imag == 0 -> the real epilogue's alpha;  otherwise folded into the expansion pass of B
+//   beta : imag == 0 -> the real epilogue's beta;   otherwise C *= beta first (one streaming pass), then beta' = 1
+static bool imag_is_zero(int32_t base, const void *cx) {
+    const size_t s = real_dtype_size(base);
+    const unsigned char *p = (const unsigned char *)cx + s;
+    if (base == 8) return load_host<float>(p) == 0.0f;   // -0.0 counts as zero
+    if (base == 9) return load_host<double>(p) == 0.0;
+    for (size_t i = 0; i < s; i++)
+        if (p[i]) return false;
+    return true;
+}
+
+static int32_t gemm_complex(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K,
+                            const void *alpha, const void *A, uint64_t lda, const void *B, uint64_t ldb, const void *beta, void *C,
+                            uint64_t ldc) {
+    if (!A || !B || !C) {
+        set_error("gemm: null buffer");
+        return WK_ERR_INVALID_BUFFER;
+    }
+    if (M == 0 || N == 0 || K == 0 || (op_a & ~1) || (op_b & ~1)) {
+        set_error("gemm: invalid shape/op");
+        return WK_ERR_INVALID_VALUE;
+    }
+    const uint64_t a_cols = op_a ? M : K, b_cols = op_b ? K : N, a_rows = op_a ? K : M, b_rows = op_b ? N : K;
+    if (lda < a_cols || ldb < b_cols || ldc < N) {
+        set_error("gemm: pitch smaller than row length");
+        return WK_ERR_INVALID_VALUE;
+    }
+    const int32_t base = dtype - 10;
+    const size_t es = real_dtype_size(base);
+    const uint64_t align_el = 16 / es;  // workspace pitches keep every row 16-byte aligned (TMA / cp.async)
+    auto round_up = [&](uint64_t v) { return (v + align_el - 1) / align_el * align_el; };
+    const uint64_t ldb2 = round_up(2 * b_cols);                  // expanded B: [2*b_rows, 2*b_cols] reals
+    const uint64_t lda2 = op_a ? round_up(a_cols) : 2 * lda;     // split A: [2*K, M] reals; op_a = N: storage in place
+    const size_t b_bytes = (size_t)(2 * b_rows) * ldb2 * es;
+    const size_t b_bytes_al = (b_bytes + 255) / 256 * 256;
+    const size_t a_bytes = op_a ? (size_t)(2 * a_rows) * lda2 * es : 0;
+    int32_t rc = ensure_workspace(q, b_bytes_al + a_bytes);
+    if (rc != WK_OK) return rc;
+    void *B2 = q->ws;
+    void *A2 = op_a ? (void *)((char *)q->ws + b_bytes_al) : const_cast<void *>(A);
+
+    const bool fold_alpha = alpha && !imag_is_zero(base, alpha);
+    rc = cx_expand_b(q, base, op_b, b_rows, b_cols, B, ldb, B2, ldb2, fold_alpha ? alpha : nullptr);
+    if (rc != WK_OK) return rc;
+    if (op_a) {
+        rc = cx_split_a(q, base, a_rows, a_cols, A, lda, A2, lda2);
+        if (rc != WK_OK) return rc;
+    }
+    // real scalars for the epilogue: one host element of the base type (the .re component when imag == 0)
+    unsigned char one[8] = {0};
+    if (base == 8) { const float f = 1.0f; memcpy(one, &f, 4); }
+    else if (base == 9) { const double d = 1.0; memcpy(one, &d, 8); }
+    else one[0] = 1;  // little-endian integer 1 of any width
+    const void *r_alpha = alpha ? (fold_alpha ? (const void *)one : alpha) : nullptr;
+    const void *r_beta = beta;
+    if (beta && !imag_is_zero(base, beta)) {
+        rc = wk_scal(q, dtype, 1, M, N, beta, C, ldc, ldc * M);
+        if (rc != WK_OK) return rc;
+        r_beta = one;
+    }
+    return gemm_any(q, base, op_a, op_b, M, 2 * N, 2 * K, r_alpha, A2, lda2, B2, ldb2, r_beta, C, 2 * ldc, nullptr, WK_ACT_NONE,
+                    nullptr);
+}
 }  // namespace wk
 
 using namespace wk;
@@ -72,10 +139,11 @@ WK_API int32_t wk_gemm(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, u
                        const void *alpha, const void *A, uint64_t lda, const void *B, uint64_t ldb, const void *beta, void *C,
                        uint64_t ldc) {
     WK_CHECK_QUEUE(q);
-    if (dtype < 0 || dtype > 9) {
+    if (dtype < 0 || dtype > 19) {
         set_error("gemm: dtype %d not supported", dtype);
         return WK_ERR_TYPE_NOT_SUPPORTED;
     }
+    if (dtype >= 10) return gemm_complex(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     return gemm_any(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, WK_ACT_NONE, nullptr);
 }
 

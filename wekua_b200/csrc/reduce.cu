@@ -14,6 +14,18 @@ template <typename A> __device__ __forceinline__ A shfl_xor(A v, int m) { return
 template <> __device__ __forceinline__ uint64_t shfl_xor<uint64_t>(uint64_t v, int m) {
     return (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
 }
+// complex: the two components reduce independently (sum.cl:17-24)
+#define WK_SHFL_CX(AT)                                                                         \
+    template <> __device__ __forceinline__ CxAcc<AT> shfl_xor<CxAcc<AT>>(CxAcc<AT> v, int m) { \
+        return CxAcc<AT>{shfl_xor<AT>(v.re, m), shfl_xor<AT>(v.im, m)};                        \
+    }
+WK_SHFL_CX(uint32_t)
+WK_SHFL_CX(uint64_t)
+WK_SHFL_CX(float)
+WK_SHFL_CX(double)
+#undef WK_SHFL_CX
+template <typename A> struct AccZero { __device__ __forceinline__ static A get() { return (A)0; } };
+template <typename AB> struct AccZero<CxAcc<AB>> { __device__ __forceinline__ static CxAcc<AB> get() { return CxAcc<AB>{(AB)0, (AB)0}; } };
 
 template <typename A> __device__ __forceinline__ A block_reduce_sum(A v) {
     __shared__ A warp_part[kRThreads / 32];
@@ -22,9 +34,9 @@ template <typename A> __device__ __forceinline__ A block_reduce_sum(A v) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) warp_part[warp] = v;
     __syncthreads();
-    A r = (A)0;
+    A r = AccZero<A>::get();
     if (warp == 0) {
-        r = lane < kRThreads / 32 ? warp_part[lane] : (A)0;
+        r = lane < kRThreads / 32 ? warp_part[lane] : AccZero<A>::get();
 #pragma unroll
         for (int m = 4; m >= 1; m >>= 1) r = r + shfl_xor<A>(r, m);
     }
@@ -42,7 +54,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restr
     using A = typename Acc<T>::type;
     constexpr int VEC = 16 / (int)sizeof(T);
     union Pack { uint4 u; T e[VEC]; };
-    A acc[4] = {(A)0, (A)0, (A)0, (A)0};
+    A acc[4] = {AccZero<A>::get(), AccZero<A>::get(), AccZero<A>::get(), AccZero<A>::get()};
     for (uint64_t r = blockIdx.y; r < n_runs; r += gridDim.y) {
         const uint64_t d = r / rows, j = r - d * rows;
         const T *xr = x + d * xsp + j * xrp;
@@ -89,7 +101,7 @@ template <typename T>
 __global__ void __launch_bounds__(kRThreads) reduce_final_kernel(const typename Acc<T>::type *__restrict__ partial,
                                                                  uint64_t n, T *__restrict__ out) {
     using A = typename Acc<T>::type;
-    A v = (A)0;
+    A v = AccZero<A>::get();
     for (uint64_t i = threadIdx.x; i < n; i += kRThreads) v = v + partial[i];
     v = block_reduce_sum<A>(v);
     if (threadIdx.x == 0) *out = from_acc<T>(v);
@@ -131,7 +143,7 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     WK_CHECK_LAUNCH();
     WK_CUDA(cudaMemcpyAsync(q->pinned, result, sizeof(T), cudaMemcpyDeviceToHost, q->stream));
     WK_CUDA(cudaStreamSynchronize(q->stream));
-    *(T *)host_out = *(const T *)q->pinned;
+    memcpy(host_out, q->pinned, sizeof(T));
     return WK_OK;
 }
 
@@ -174,7 +186,7 @@ using namespace wk;
 WK_API int32_t wk_sum(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t row_pitch, uint64_t slice_pitch,
                       const void *x, void *host_out) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         return reduce_runs<scalar_t, 1>(q, (const scalar_t *)x, nullptr, depth, rows, row_pitch, row_pitch, slice_pitch, 0, 0,
                                         host_out);
     });
@@ -183,7 +195,7 @@ WK_API int32_t wk_sum(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows,
 WK_API int32_t wk_dot_reduce(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *x,
                              uint64_t xrp, uint64_t xsp, const void *y, uint64_t yrp, uint64_t ysp, void *host_out) {
     WK_CHECK_QUEUE(q);
-    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         return reduce_runs<scalar_t, 2>(q, (const scalar_t *)x, (const scalar_t *)y, depth, rows, cols, xrp, xsp, yrp, ysp,
                                         host_out);
     });

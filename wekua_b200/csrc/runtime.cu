@@ -42,6 +42,19 @@ int32_t ensure_scratch(wk_queue *q, size_t bytes) {
     return WK_OK;
 }
 
+int32_t ensure_workspace(wk_queue *q, size_t bytes) {
+    if (q->ws_bytes >= bytes) return WK_OK;
+    if (q->ws) {
+        WK_CUDA(cudaStreamSynchronize(q->stream));
+        WK_CUDA(cudaFree(q->ws));
+        q->ws = nullptr;
+        q->ws_bytes = 0;
+    }
+    WK_CUDA(cudaMalloc(&q->ws, bytes));
+    q->ws_bytes = bytes;
+    return WK_OK;
+}
+
 static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t adopt) {
     q->device = device;
     q->wekua_id = wekua_id;
@@ -63,6 +76,9 @@ static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t ad
 static void queue_fini(wk_queue *q) {
     cudaSetDevice(q->device);
     if (q->scratch) cudaFree(q->scratch);
+    if (q->ws) cudaFree(q->ws);
+    q->ws = nullptr;
+    q->ws_bytes = 0;
     if (q->pinned) cudaFreeHost(q->pinned);
     if (q->owns_stream && q->stream) cudaStreamDestroy(q->stream);
     q->scratch = nullptr;

@@ -38,11 +38,21 @@ def mean(pipeline: Pipeline, x: Tensor):
     """math.mean, basic.zig:206-240: @divTrunc for ints, / for floats, by the UNPADDED element count"""
     s = sum(pipeline, x)
     n = x.number_of_elements_without_padding
-    if x.dtype.kind == "f":
-        return x.dtype.type(s / x.dtype.type(n))
+    if x.dtype.names is not None:  # complex: each component on its own (basic.zig:216-227)
+        out = np.zeros((), dtype=x.dtype)
+        for comp in ("re", "im"):
+            out[comp] = _mean_component(s[comp], n)
+        return out[()]
+    return _mean_component(s, n)
+
+
+def _mean_component(s, n):
+    dt = np.dtype(type(s))
+    if dt.kind == "f":
+        return dt.type(s / dt.type(n))
     si, ni = int(s), int(n)
     q = abs(si) // ni
-    return x.dtype.type(q if si >= 0 else -q)
+    return dt.type(q if si >= 0 else -q)
 
 
 def _unary(name):

@@ -10,7 +10,7 @@ import time
 import numpy as np
 
 from . import capi
-from .core import Context, Pipeline, get_type_index
+from .core import Context, Pipeline, as_elements, base_type, get_type_index, storage_dtype
 
 
 def _np_ptr(a: np.ndarray):
@@ -21,7 +21,7 @@ def _scalar(dtype, v):
     """pointer to one host element of the tensor's type, or None for Zig `null`"""
     if v is None:
         return None, None
-    a = np.array([v]).astype(dtype)
+    a = as_elements(v, dtype).reshape(1)
     return a, _np_ptr(a)
 
 
@@ -39,7 +39,7 @@ class Tensor:
         if len(shape) == 0 or any(s == 0 for s in shape):
             raise capi.InvalidValue("InvalidValue: empty shape / zero dimension")
         self.context = context
-        self.dtype = np.dtype(dtype)
+        self.dtype = storage_dtype(dtype)
         self.type_index = get_type_index(dtype)
         self.shape = tuple(shape)
         # main.zig:142-150: vector width = max over the context's queues (all 1 on the CUDA backend)
@@ -147,7 +147,7 @@ class memory:
     def read_from_buffer(pipeline: Pipeline, tensor: Tensor, buffer) -> None:
         """memory.readFromBuffer (host -> tensor), read_from_buffer.zig:13-63.  The host array must stay alive
         until the pipeline is waited on (same lifetime rule as the reference's non-blocking writeRect)."""
-        host = np.ascontiguousarray(buffer, dtype=tensor.dtype).reshape(-1)
+        host = as_elements(buffer, tensor.dtype).reshape(-1)
         if host.size != tensor.number_of_elements_without_padding:
             raise capi.InvalidBuffer("InvalidBuffer")
         es = tensor.dtype.itemsize
@@ -269,7 +269,7 @@ class random:
         """random.uniform (uniform.zig:60-123); seed None = wall clock (uniform.zig:82)"""
         if seed is None:
             seed = int(time.time())
-        a, pa = _scalar(tensor.dtype, min_value)
-        b, pb = _scalar(tensor.dtype, max_value)
+        a, pa = _scalar(base_type(tensor.dtype), min_value)  # bounds are scalars of the base type (uniform.zig:64-65)
+        b, pb = _scalar(base_type(tensor.dtype), max_value)
         capi.check(capi.lib().wk_uniform(pipeline.q, tensor.type_index, tensor.depth, tensor.rows, tensor.cols, tensor.ptr,
                                          tensor.row_pitch, tensor.slice_pitch, C.c_uint64(seed & (2**64 - 1)), pa, pb))
