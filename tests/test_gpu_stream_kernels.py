@@ -1,0 +1,81 @@
+"""-m gpu: the bandwidth-tuned variants of bias add (bias.cl), bias step (bias_step.cl) and the 2-D transpose
+(transpose.cl) at sizes where the 128-bit / multi-chunk code paths are taken, against the oracle (bias kernels) and
+numpy (transpose is a permutation: bit-exact for every element size)."""
+import numpy as np
+import pytest
+
+from . import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+FLOATS = [np.float32, np.float64]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import pyoracle
+
+    return pyoracle
+
+
+@pytest.mark.parametrize("dtype", FLOATS)
+@pytest.mark.parametrize("shape", [(2, 4), (3, 5), (64, 36), (1000, 36), (513, 1028), (4096, 1024), (7, 30002)])
+def test_bias_add_exact(oracle, dtype, shape):
+    """out[i] += bias[i % row_pitch] over the whole padded buffer (bias.cl:3-19): one IEEE add per element => bit-exact"""
+    wk = gh.wk()
+    _, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(5)
+    out, oout = gh.make_pair(oracle, dtype, shape, rng.uniform(-3, 3, shape))
+    bias, obias = gh.make_pair(oracle, dtype, (shape[1],), rng.uniform(-1, 1, shape[1]))
+    wk.nn.Linear._add_bias(pipe, out, bias)
+    oracle.bias(oout, obias)
+    np.testing.assert_array_equal(gh.padded(out), oout.buf)
+    for t in (out, bias):
+        t.release(pipe)
+
+
+@pytest.mark.parametrize("dtype", FLOATS)
+@pytest.mark.parametrize("shape", [(2, 4), (256, 36), (256, 1028), (1000, 36), (5000, 1028), (32768, 256), (300, 30002)])
+def test_bias_step(oracle, dtype, shape):
+    """column sums (bias_step.cl:24-37): rows <= 256 are summed in the reference's order (bit-exact); taller inputs are
+    split into row chunks (deterministic, different association) and agree within rows*eps*sum|x|"""
+    wk = gh.wk()
+    _, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(6)
+    data = rng.uniform(-1, 1, shape).astype(dtype)
+    sens, osens = gh.make_pair(oracle, dtype, shape, data)
+    bg, obg = gh.make_pair(oracle, dtype, (shape[1],))
+    wk.nn.Linear._bias_sensitivity(pipe, sens, bg)
+    oracle.bias_step(osens, obg)
+    got, want = gh.to_np(bg), obg.to_host()
+    if shape[0] <= 256:
+        np.testing.assert_array_equal(got, want)
+    else:
+        bound = shape[0] * np.finfo(dtype).eps * np.abs(data.astype(np.float64)).sum(axis=0)
+        assert np.all(np.abs(got.astype(np.float64) - data.astype(np.float64).sum(axis=0)) <= bound)
+        assert np.all(np.abs(want.astype(np.float64) - data.astype(np.float64).sum(axis=0)) <= bound)
+    # twice the same launch => the same bits (no atomics)
+    bg2, _ = gh.make_pair(oracle, dtype, (shape[1],))
+    wk.nn.Linear._bias_sensitivity(pipe, sens, bg2)
+    np.testing.assert_array_equal(gh.to_np(bg2), got)
+    for t in (sens, bg, bg2):
+        t.release(pipe)
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.uint16, np.float32, np.int64, np.float64])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 2048), (1000, 36), (516, 1028), (2050, 130), (33, 77), (4096, 4096)])
+def test_transpose2d_exact(dtype, shape):
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(7)
+    data = gh.rand_data(rng, dtype, shape)
+    a = wk.Tensor.alloc(ctx, pipe, shape, dtype)
+    b = wk.Tensor.alloc(ctx, pipe, shape[::-1], dtype)
+    wk.tensor.memory.read_from_buffer(pipe, a, data)
+    wk.tensor.transpose(pipe, b, a, 0, 1)
+    np.testing.assert_array_equal(gh.to_np(b), data.T)
+    # padding of the destination stays zero
+    pad = gh.padded(b).reshape(b.rows_padded, b.row_pitch)
+    assert not pad[b.rows:, :].any() and not pad[:, b.cols:].any()
+    for t in (a, b):
+        t.release(pipe)

@@ -375,16 +375,48 @@ template <typename BT, bool RANGE> struct UniformF<Cx<BT>, RANGE> {
     }
 };
 
-// bias.cl:3-19: out[i] += bias[i % row_pitch].  Treated as a [n/rp, rp] matrix: a thread owns a 128-bit column
-// group, loads its bias values once and walks down the rows -- no per-element modulo.
-template <typename T>
-__global__ void __launch_bounds__(kThreads) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias,
-                                                            uint64_t rp, uint64_t n_rows, uint64_t tail) {
-    const uint64_t col = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (col < rp) {
-        const T b = bias[col];
-        for (uint64_t r = blockIdx.y; r < n_rows; r += gridDim.y) out[r * rp + col] += b;
-        if (blockIdx.y == 0 && col < tail) out[n_rows * rp + col] += b;  // partial last row (n % rp)
+// bias.cl:3-19: out[i] += bias[i % row_pitch], i < n.  Flat streaming over the buffer like map_vec_kernel (128-bit
+// accesses, kUnroll vectors in flight per thread); each thread tracks the bias column of its vectors incrementally --
+// one 64-bit modulo before the loop, an add and a conditional subtract per step -- and reads bias through L1.
+// VECTOR = false is the same loop over single elements (row pitch or n not a multiple of the vector width).
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(kThreads) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias, uint64_t rp_units,
+                                                            uint64_t n_units) {
+    constexpr int VEC = VECTOR ? 16 / (int)sizeof(T) : 1;
+    union Pack { uint4 u; T e[16 / sizeof(T)]; };
+    const uint64_t chunk = (uint64_t)kThreads * kUnroll;
+    const uint64_t step = (uint64_t)gridDim.x * chunk;
+    const uint64_t step_mod = step % rp_units;
+    uint64_t col[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) col[u] = ((uint64_t)blockIdx.x * chunk + (uint64_t)u * kThreads + threadIdx.x) % rp_units;
+    for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < n_units; base += step) {
+        Pack o[kUnroll], b[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_units) {
+                if (VECTOR) {
+                    o[u].u = ld_rw(reinterpret_cast<const uint4 *>(out) + vi);
+                    b[u].u = __ldg(reinterpret_cast<const uint4 *>(bias) + col[u]);
+                } else {
+                    o[u].e[0] = out[vi];
+                    b[u].e[0] = __ldg(bias + col[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_units) {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) o[u].e[e] += b[u].e[e];
+                if (VECTOR) st_na(reinterpret_cast<uint4 *>(out) + vi, o[u].u);
+                else out[vi] = o[u].e[0];
+            }
+            col[u] += step_mod;
+            if (col[u] >= rp_units) col[u] -= rp_units;
+        }
     }
 }
 
@@ -407,6 +439,43 @@ __global__ void __launch_bounds__(256) transpose2d_kernel(const T *__restrict__ 
     for (int j = threadIdx.y; j < 32; j += 8) {
         const uint64_t c = c0 + j, r = r0 + threadIdx.x;
         if (r < rows && c < cols) dst[c * dp + r] = tile[threadIdx.x][j];
+    }
+}
+
+// 64 x 64 tile, 128-bit global accesses on both sides (kIter vectors in flight per thread), elements cross over through
+// a padded shared tile with scalar accesses (2-way bank conflicts at worst, far below the HBM time of the tile).
+// Needs rows, cols and both pitches to be multiples of the vector width and 16-byte aligned pointers.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose2d_vec_kernel(const T *__restrict__ src, uint64_t sp, T *__restrict__ dst,
+                                                              uint64_t dp, uint64_t rows, uint64_t cols) {
+    constexpr int VEC = 16 / (int)sizeof(T), TS = 64, VPR = TS / VEC, ITER = TS * VPR / 256;
+    __shared__ T tile[TS][TS + 1];
+    union Pack { uint4 u; T e[VEC]; };
+    const uint64_t c0 = (uint64_t)blockIdx.x * TS, r0 = (uint64_t)blockIdx.y * TS;
+    Pack in[ITER];
+#pragma unroll
+    for (int k = 0; k < ITER; k++) {
+        const int v = k * 256 + threadIdx.x, r = v / VPR, cv = v % VPR;
+        const uint64_t gr = r0 + r, gc = c0 + (uint64_t)cv * VEC;
+        if (gr < rows && gc < cols) in[k].u = ld_ro(reinterpret_cast<const uint4 *>(src + gr * sp + gc));
+    }
+#pragma unroll
+    for (int k = 0; k < ITER; k++) {
+        const int v = k * 256 + threadIdx.x, r = v / VPR, cv = v % VPR;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) tile[r][cv * VEC + e] = in[k].e[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITER; k++) {
+        const int v = k * 256 + threadIdx.x, c = v / VPR, rv = v % VPR;
+        const uint64_t gc = c0 + c, gr = r0 + (uint64_t)rv * VEC;
+        if (gc < cols && gr < rows) {
+            Pack o;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) o.e[e] = tile[rv * VEC + e][c];
+            st_na(reinterpret_cast<uint4 *>(dst + gc * dp + gr), o.u);
+        }
     }
 }
 
@@ -583,14 +652,19 @@ WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void 
     if (!output || !bias) return WK_ERR_INVALID_BUFFER;
     if (row_pitch == 0) return WK_ERR_INVALID_VALUE;
     return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
-        const uint64_t n_rows = n / row_pitch, tail = n % row_pitch;
-        uint64_t gx = (row_pitch + kThreads - 1) / kThreads;
-        uint64_t gy = n_rows == 0 ? 1 : n_rows;
-        const uint64_t want = ((uint64_t)q->sm_count * kCtasPerSm + gx - 1) / gx;
-        if (gy > want) gy = want;
-        if (gy > 65535) gy = 65535;
-        bias_add_kernel<scalar_t><<<dim3((unsigned)gx, (unsigned)gy), kThreads, 0, q->stream>>>(
-            (scalar_t *)output, (const scalar_t *)bias, row_pitch, n_rows, tail);
+        constexpr uint64_t VEC = 16 / sizeof(scalar_t);
+        const bool vec = aligned16(output) && aligned16(bias) && row_pitch % VEC == 0 && n % VEC == 0;
+        const uint64_t n_units = vec ? n / VEC : n, rp_units = vec ? row_pitch / VEC : row_pitch;
+        if (n_units == 0) return WK_OK;
+        uint64_t blocks = (n_units + (uint64_t)kThreads * kUnroll - 1) / ((uint64_t)kThreads * kUnroll);
+        const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+        if (blocks > cap) blocks = cap;
+        if (vec)
+            bias_add_kernel<scalar_t, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
+                                                                                         rp_units, n_units);
+        else
+            bias_add_kernel<scalar_t, false><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
+                                                                                          rp_units, n_units);
         WK_CHECK_LAUNCH();
         return WK_OK;
     });
@@ -687,6 +761,17 @@ WK_API int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_
     WK_CHECK_QUEUE(q);
     if (!src || !dst) return WK_ERR_INVALID_BUFFER;
     return WK_DISPATCH_SIZE(dtype, [&]() -> int32_t {
+        if constexpr (sizeof(scalar_t) <= 8) {
+            constexpr uint64_t VEC = 16 / sizeof(scalar_t);
+            if (aligned16(src) && aligned16(dst) && rows % VEC == 0 && cols % VEC == 0 && sp % VEC == 0 && dp % VEC == 0 &&
+                (rows + 63) / 64 <= 65535) {
+                dim3 vgrid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+                transpose2d_vec_kernel<scalar_t><<<vgrid, 256, 0, q->stream>>>((const scalar_t *)src, sp, (scalar_t *)dst, dp, rows,
+                                                                              cols);
+                WK_CHECK_LAUNCH();
+                return WK_OK;
+            }
+        }
         dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
         if (grid.y > 65535) {
             set_error("transpose2d: too many rows");

@@ -150,23 +150,43 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
 // bias_step.cl:24-37.  Stage 1: thread (c, chunk) sums rows [chunk*rows_per, ...) of column c in ascending row
 // order (coalesced across c); stage 2 folds the chunks in ascending order.  With one chunk the summation order
 // is exactly the reference's.
-template <typename T>
+// VECTOR: a thread owns one 128-bit group of columns (row pitch a multiple of the vector width, aligned rows) and keeps
+// 4 row vectors in flight; per column the additions are the same ones in the same order.
+template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, uint64_t rp, uint64_t rows, uint64_t n_cols,
                                                      uint64_t rows_per, T *__restrict__ out, uint64_t out_pitch) {
-    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    constexpr int VEC = VECTOR ? 16 / (int)sizeof(T) : 1;
+    union Pack { uint4 u; T e[16 / sizeof(T)]; };
+    const uint64_t c = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * VEC;
     if (c >= n_cols) return;
     const uint64_t r0 = (uint64_t)blockIdx.y * rows_per;
     uint64_t r1 = r0 + rows_per;
     if (r1 > rows) r1 = rows;
-    T acc = (T)0;
+    T acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[e] = (T)0;
     const T *p = s + r0 * rp + c;
+    auto load = [](const T *q) {
+        Pack v;
+        if (VECTOR) v.u = __ldg(reinterpret_cast<const uint4 *>(q));
+        else v.e[0] = *q;
+        return v;
+    };
     uint64_t r = r0;
     for (; r + 4 <= r1; r += 4, p += 4 * rp) {  // 4 loads in flight, summed in order
-        const T a0 = p[0], a1 = p[rp], a2 = p[2 * rp], a3 = p[3 * rp];
-        acc += a0; acc += a1; acc += a2; acc += a3;
+        const Pack a0 = load(p), a1 = load(p + rp), a2 = load(p + 2 * rp), a3 = load(p + 3 * rp);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) { acc[e] += a0.e[e]; acc[e] += a1.e[e]; acc[e] += a2.e[e]; acc[e] += a3.e[e]; }
     }
-    for (; r < r1; r++, p += rp) acc += *p;
-    out[(uint64_t)blockIdx.y * out_pitch + c] = acc;
+    for (; r < r1; r++, p += rp) {
+        const Pack a = load(p);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[e] += a.e[e];
+    }
+    T *o = out + (uint64_t)blockIdx.y * out_pitch + c;
+#pragma unroll
+    for (int e = 0; e < VEC; e++)
+        if (c + e < n_cols) o[e] = acc[e];
 }
 
 template <typename T>
@@ -207,29 +227,38 @@ WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *
     if (!sens || !bias_grad) return WK_ERR_INVALID_BUFFER;
     if (n_cols == 0) return WK_ERR_INVALID_VALUE;
     return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
-        const uint64_t gx = (n_cols + 255) / 256;
+        constexpr uint64_t VEC = 16 / sizeof(scalar_t);
+        // the vector kernel reads whole 128-bit column groups: the last group may reach into the row's padding columns
+        const bool vec = aligned16(sens) && row_pitch % VEC == 0 && (n_cols + VEC - 1) / VEC * VEC <= row_pitch;
+        const uint64_t col_units = vec ? (n_cols + VEC - 1) / VEC : n_cols;
+        const uint64_t gx = (col_units + 255) / 256;
         // enough chunks to fill the machine, but never split short columns (keeps the reference's order)
         uint64_t chunks = 1;
         if (rows > 256) {
-            chunks = ((uint64_t)q->sm_count * 4 + gx - 1) / gx;
+            chunks = ((uint64_t)q->sm_count * 2048 + col_units - 1) / col_units;  // ~2048 threads per SM
             const uint64_t max_chunks = (rows + 63) / 64;
             if (chunks > max_chunks) chunks = max_chunks;
             if (chunks > 65535) chunks = 65535;
             if (chunks < 1) chunks = 1;
         }
         const uint64_t rows_per = (rows + chunks - 1) / chunks;
+        auto stage1 = [&](scalar_t *out, uint64_t out_pitch) {
+            const dim3 grid((unsigned)gx, (unsigned)chunks);
+            if (vec)
+                colsum_stage1<scalar_t, true><<<grid, 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, out, out_pitch);
+            else
+                colsum_stage1<scalar_t, false><<<grid, 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, out, out_pitch);
+        };
         if (chunks == 1) {
-            colsum_stage1<scalar_t><<<dim3((unsigned)gx, 1), 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols,
-                                                                              rows_per, (scalar_t *)bias_grad, 0);
+            stage1((scalar_t *)bias_grad, 0);
             WK_CHECK_LAUNCH();
             return WK_OK;
         }
         int32_t rc = ensure_scratch(q, chunks * n_cols * sizeof(scalar_t));
         if (rc != WK_OK) return rc;
-        colsum_stage1<scalar_t><<<dim3((unsigned)gx, (unsigned)chunks), 256, 0, q->stream>>>(
-            (const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, (scalar_t *)q->scratch, n_cols);
+        stage1((scalar_t *)q->scratch, n_cols);
         WK_CHECK_LAUNCH();
-        colsum_stage2<scalar_t><<<(unsigned)gx, 256, 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
+        colsum_stage2<scalar_t><<<(unsigned)((n_cols + 255) / 256), 256, 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
                                                                     (scalar_t *)bias_grad);
         WK_CHECK_LAUNCH();
         return WK_OK;

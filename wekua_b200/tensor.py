@@ -44,6 +44,7 @@ class Tensor:
         self.shape = tuple(shape)
         # main.zig:142-150: vector width = max over the context's queues (all 1 on the CUDA backend)
         vw = 1
+        vectors_enabled = vectors_enabled and self.type_index < 10  # main.zig:141: complex tensors are never vectorised
         if vectors_enabled:
             for cq in context.command_queues:
                 vw = max(vw, int(cq.vector_widths[self.type_index]))
