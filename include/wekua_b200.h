@@ -12,7 +12,9 @@
  *  - every function returns an int32 status (WK_OK == 0); the Zig shim maps it onto the TensorErrors
  *    error set of src/tensor/main.zig:25-33.
  *  - `dtype` is core.types.getTypeIndex (src/core/types.zig:60-87): 0 i8, 1 u8, 2 i16, 3 u16, 4 i32, 5 u32,
- *    6 i64, 7 u64, 8 f32, 9 f64.  Complex ids 10-19 return WK_ERR_TYPE_NOT_SUPPORTED (not in scope yet).
+ *    6 i64, 7 u64, 8 f32, 9 f64; 10-19 = Complex(T) of 0-9 (types.zig:74-83: {real, imag} stored next to each other).
+ *    Complex is accepted wherever the reference compiles a complex branch (gemm, axpy, dot, sum, trig, fill, identity,
+ *    uniform, transpose); the nn kernels are f32/f64 only like the reference (TypeNotSupported otherwise).
  *  - scalars (alpha, beta, lr ...) are passed by pointer to ONE host value of the element type; a NULL
  *    pointer is Zig's `null` (src/blas/gemm.zig:834-874: beta == null overwrites C, alpha == null means 1).
  *  - pitches / leading dimensions are in ELEMENTS, exactly the numbers the reference passes to its kernels
@@ -171,6 +173,14 @@ int32_t wk_hadamard(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, u
  * reference's row loop runs over the PADDED row, sum.cl:33-35).  Blocking; result to *host_out. */
 int32_t wk_sum(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t row_pitch, uint64_t slice_pitch,
                const void *x, void *host_out);
+/* the same reductions with the scalar left in DEVICE memory (one element of `dtype` at device_out) and no host
+ * synchronisation: lets a loss value feed later kernels / be read back once per epoch instead of once per step
+ * (the reference blocks on a mapped read inside every math.sum, basic.zig:154-171). */
+int32_t wk_sum_async(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t row_pitch, uint64_t slice_pitch,
+                     const void *x, void *device_out);
+int32_t wk_dot_reduce_async(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *x,
+                            uint64_t x_row_pitch, uint64_t x_slice_pitch, const void *y, uint64_t y_row_pitch,
+                            uint64_t y_slice_pitch, void *device_out);
 /* sin|cos|tan|sinh|cosh|tanh (src/math/trig.zig:15-113) and Sigmoid.run (src/nn/activation/sigmoid.zig:39-96):
  * in place over n contiguous elements (the reference launches over the whole padded buffer). f32/f64. */
 int32_t wk_unary(wk_queue *q, int32_t dtype, int32_t op, void *x, uint64_t n);
@@ -199,6 +209,23 @@ int32_t wk_rmsprop(wk_queue *q, int32_t dtype, void *x, const void *grad, void *
 /* Adam does not exist in src/ (adam.zig is empty); textbook bias-corrected Adam, step t >= 1. parity unpinned */
 int32_t wk_adam(wk_queue *q, int32_t dtype, void *x, const void *grad, void *m, void *v, const void *lr,
                 const void *beta1, const void *beta2, const void *eps, uint64_t t, uint64_t n);
+
+/* One launch for the whole parameter list of Optimizer.step (gd.zig:55-94, gdm.zig, adagrad.zig, rmsprop.zig:168-202
+ * walk cache.slots and enqueue one kernel per weight / bias tensor).  Element-wise results are
+ * bit-identical to the per-tensor entries above.  kind GD: x += lr * grad with the axpy rules (lr is the value GD.init
+ * stores, i.e. -config.lr; lr == -1 takes the subtract form); state0/state1 are velocity | history | (m, v).
+ * n = contiguous elements of each buffer (the reference launches these kernels over the whole padded buffer). */
+typedef struct {
+    void *x;            /* parameter tensor (weights or bias) */
+    const void *grad;   /* its gradient */
+    void *state0;       /* GDM velocity / Adagrad, RMSProp history / Adam m; NULL for GD */
+    void *state1;       /* Adam v; NULL otherwise */
+    uint64_t n;
+} wk_opt_param_t;
+enum { WK_OPT_GD = 0, WK_OPT_GDM = 1, WK_OPT_ADAGRAD = 2, WK_OPT_RMSPROP = 3, WK_OPT_ADAM = 4 };
+int32_t wk_optimizer_step_multi(wk_queue *q, int32_t dtype, int32_t kind, const wk_opt_param_t *params, uint32_t n_params,
+                                const void *lr, const void *h0 /* beta | gamma | beta1 */, const void *h1 /* beta2 */,
+                                const void *h2 /* eps */, uint64_t t /* Adam step >= 1 */);
 
 /* -------------------------------------------------------------------------------- tensor utilities */
 /* fill.constant src/tensor/fill.zig:15-70 + fill.cl (logical region only) */

@@ -76,6 +76,19 @@ def test_host_layout_math_equals_reference_restatement(oracle, dtype):
         assert t.number_of_elements_without_padding == o.number_of_elements_without_padding
 
 
+def test_host_layout_math_complex(oracle):
+    """complex tensors are never vectorised (main.zig:141) and their type ids 10-19 lie past vector_widths[10]"""
+    from wekua_b200 import Tensor, core
+
+    dev = oracle.device("b200")
+    for dtype in (np.complex64, np.complex128, core.Complex(np.int16)):
+        for shape in [(5,), (4, 1), (5, 7), (2, 3, 4)]:
+            t = Tensor.wrap(_FakeCtx(), None, shape, dtype, device_ptr=0)
+            o = oracle.OTensor(dev, dtype, shape).layout
+            assert not t.vectors_enabled and t.vector_width == 1
+            assert (t.row_pitch, t.slice_pitch, t.number_of_elements) == (o.row_pitch, o.slice_pitch, o.number_of_elements)
+
+
 def test_gemm_validation_is_host_side():
     """validateTensors (gemm.zig:442-485) and PackedTensors.validateTensors (:250-270) run before any launch"""
     from wekua_b200 import Tensor, blas, capi

@@ -64,6 +64,11 @@ class QueueInfo(C.Structure):
     ]
 
 
+class OptParam(C.Structure):
+    """wk_opt_param_t: one (parameter, gradient, state) record of wk_optimizer_step_multi"""
+    _fields_ = [("x", C.c_void_p), ("grad", C.c_void_p), ("state0", C.c_void_p), ("state1", C.c_void_p), ("n", C.c_uint64)]
+
+
 _u64, _i32, _vp, _sz = C.c_uint64, C.c_int32, C.c_void_p, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
 
@@ -109,6 +114,8 @@ SIGNATURES = {
     "wk_dot_reduce": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _vp, _u64, _u64, _vp],
     "wk_hadamard": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _vp, _u64, _u64],
     "wk_sum": [_vp, _i32, _u64, _u64, _u64, _u64, _vp, _vp],
+    "wk_sum_async": [_vp, _i32, _u64, _u64, _u64, _u64, _vp, _vp],
+    "wk_dot_reduce_async": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _vp, _u64, _u64, _vp],
     "wk_unary": [_vp, _i32, _i32, _vp, _u64],
     "wk_sigmoid_dev": [_vp, _i32, _vp, _vp, _u64],
     "wk_tanh_dev": [_vp, _i32, _vp, _vp, _u64],
@@ -120,6 +127,7 @@ SIGNATURES = {
     "wk_adagrad": [_vp, _i32, _vp, _vp, _vp, _vp, _u64],
     "wk_rmsprop": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _u64],
     "wk_adam": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64],
+    "wk_optimizer_step_multi": [_vp, _i32, _i32, C.POINTER(OptParam), C.c_uint32, _vp, _vp, _vp, _vp, _u64],
     "wk_fill": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _vp],
     "wk_identity": [_vp, _i32, _vp, _u64, _u64, _u64],
     "wk_uniform": [_vp, _i32, _u64, _u64, _u64, _vp, _u64, _u64, _u64, _vp, _vp],

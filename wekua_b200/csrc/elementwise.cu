@@ -500,6 +500,119 @@ __global__ void __launch_bounds__(256) transpose_nd_kernel(const T *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------- multi-tensor apply
+// One launch over a LIST of tensors (Optimizer.step walks every weight / bias tensor of every layer and enqueues one
+// kernel each, rmsprop.zig:168-202).  The list travels in the kernel parameters; work is cut into chunks of
+// kThreads*kUnroll vectors, chunk ids are global over the list (prefix sums in the table) and blocks grid-stride over
+// them, so a list of tiny tensors costs one launch and a list of huge ones streams exactly like map_vec_kernel.
+constexpr int kMtMax = 24;
+template <int NP> struct MtTable {
+    void *p[NP][kMtMax];
+    uint64_t n[kMtMax];
+    uint64_t first_chunk[kMtMax + 1];
+    int count;
+};
+
+template <typename T, int NP, typename F>
+__global__ void __launch_bounds__(kThreads) mt_map_kernel(const __grid_constant__ MtTable<NP> tab, F f) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    union Pack { uint4 u; T e[VEC]; };
+    constexpr uint64_t chunk_vecs = (uint64_t)kThreads * kUnroll;
+    const uint64_t total = tab.first_chunk[tab.count];
+    int t = 0;
+    for (uint64_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        while (tab.first_chunk[t + 1] <= chunk) t++;  // chunk ids only grow within a block
+        const uint64_t n = tab.n[t], n_vec = n / VEC;
+        const uint64_t base = (chunk - tab.first_chunk[t]) * chunk_vecs;
+        Pack reg[NP][kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_vec) {
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (F::kRead & (1u << p)) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(tab.p[p][t]) + vi;
+                        reg[p][u].u = (F::kWrite & (1u << p)) ? ld_rw(src) : ld_ro(src);
+                    }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
+            if (vi < n_vec) {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    T v[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) v[p] = reg[p][u].e[e];
+                    f(v, vi * VEC + e);
+#pragma unroll
+                    for (int p = 0; p < NP; p++) reg[p][u].e[e] = v[p];
+                }
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (F::kWrite & (1u << p)) st_na(reinterpret_cast<uint4 *>(tab.p[p][t]) + vi, reg[p][u].u);
+            }
+        }
+        // the tensor's last chunk also owns its tail of fewer than VEC elements
+        if (chunk + 1 == tab.first_chunk[t + 1]) {
+            const uint64_t i = n_vec * VEC + threadIdx.x;
+            if (i < n) {
+                T v[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (F::kRead & (1u << p)) v[p] = reinterpret_cast<const T *>(tab.p[p][t])[i];
+                f(v, i);
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (F::kWrite & (1u << p)) reinterpret_cast<T *>(tab.p[p][t])[i] = v[p];
+            }
+        }
+    }
+}
+
+// ptr_of(param, slot) picks the buffer of pointer slot `slot` (functor order); lists longer than kMtMax take several launches
+template <typename T, int NP, typename F, typename PtrOf>
+static int32_t launch_mt(wk_queue *q, const wk_opt_param_t *params, uint32_t n_params, F f, PtrOf ptr_of) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr uint64_t chunk_elems = (uint64_t)kThreads * kUnroll * VEC;
+    for (uint32_t first = 0; first < n_params;) {
+        MtTable<NP> tab{};
+        uint64_t chunks = 0;
+        while (first < n_params && tab.count < kMtMax) {
+            const wk_opt_param_t &pr = params[first++];
+            if (pr.n == 0) continue;
+            for (int p = 0; p < NP; p++) {
+                void *ptr = ptr_of(pr, p);
+                if (!ptr) {
+                    set_error("optimizer_step_multi: null buffer in parameter %u", first - 1);
+                    return WK_ERR_INVALID_BUFFER;
+                }
+                if (!aligned16(ptr)) {
+                    set_error("optimizer_step_multi: buffers must be 16-byte aligned (wk_malloc's are)");
+                    return WK_ERR_INVALID_VALUE;
+                }
+                tab.p[p][tab.count] = ptr;
+            }
+            tab.n[tab.count] = pr.n;
+            tab.first_chunk[tab.count] = chunks;
+            uint64_t c = (pr.n + chunk_elems - 1) / chunk_elems;
+            chunks += c;
+            tab.count++;
+        }
+        if (tab.count == 0) continue;
+        tab.first_chunk[tab.count] = chunks;
+        for (int i = tab.count + 1; i <= kMtMax; i++) tab.first_chunk[i] = chunks;
+        uint64_t blocks = chunks;
+        const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+        if (blocks > cap) blocks = cap;
+        mt_map_kernel<T, NP, F><<<(unsigned)blocks, kThreads, 0, q->stream>>>(tab, f);
+        WK_CHECK_LAUNCH();
+    }
+    return WK_OK;
+}
+
 // axpy.zig:66-91 isSubstracting
 template <typename T> static bool is_subtracting(const void *alpha) {
     if (std::is_unsigned<T>::value) return false;
@@ -781,5 +894,44 @@ WK_API int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_
                                                                         rows, cols);
         WK_CHECK_LAUNCH();
         return WK_OK;
+    });
+}
+
+WK_API int32_t wk_optimizer_step_multi(wk_queue *q, int32_t dtype, int32_t kind, const wk_opt_param_t *params, uint32_t n_params,
+                                       const void *lr, const void *h0, const void *h1, const void *h2, uint64_t t) {
+    WK_CHECK_QUEUE(q);
+    if (n_params == 0) return WK_OK;
+    if (!params) return WK_ERR_INVALID_BUFFER;
+    if (!lr) return WK_ERR_INVALID_VALUE;
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        using S = scalar_t;
+        auto xgs = [](const wk_opt_param_t &p, int slot) -> void * {  // {x, g, state0, state1}
+            return slot == 0 ? p.x : slot == 1 ? const_cast<void *>(p.grad) : slot == 2 ? p.state0 : p.state1;
+        };
+        switch (kind) {
+            case WK_OPT_GD: {  // blas.axpy(g, lr, w): pointer order {x = g, y = w}, the three variants of axpy.cl
+                auto gw = [](const wk_opt_param_t &p, int slot) -> void * { return slot == 0 ? const_cast<void *>(p.grad) : p.x; };
+                if (is_sub<S>(lr)) return launch_mt<S, 2>(q, params, n_params, AxpyF<S, 2>{acc_zero<S>()}, gw);
+                return launch_mt<S, 2>(q, params, n_params, AxpyF<S, 1>{load_scalar<S>(lr)}, gw);
+            }
+            case WK_OPT_GDM:
+                if (!h0) return WK_ERR_INVALID_VALUE;
+                return launch_mt<S, 3>(q, params, n_params, GdmF<S>{*(const S *)lr, *(const S *)h0}, xgs);
+            case WK_OPT_ADAGRAD:
+                return launch_mt<S, 3>(q, params, n_params, AdagradF<S>{*(const S *)lr}, xgs);
+            case WK_OPT_RMSPROP:
+                if (!h0) return WK_ERR_INVALID_VALUE;
+                return launch_mt<S, 3>(q, params, n_params, RmspropF<S>{*(const S *)lr, *(const S *)h0}, xgs);
+            case WK_OPT_ADAM: {
+                if (!h0 || !h1 || !h2 || t == 0) return WK_ERR_INVALID_VALUE;
+                const double B1 = (double)*(const S *)h0, B2 = (double)*(const S *)h1;
+                AdamF<S> f{*(const S *)lr, *(const S *)h0, *(const S *)h1, *(const S *)h2,
+                           (S)(1.0 / (1.0 - pow(B1, (double)t))), (S)(1.0 / (1.0 - pow(B2, (double)t)))};
+                return launch_mt<S, 4>(q, params, n_params, f, xgs);
+            }
+            default:
+                set_error("optimizer_step_multi: unknown kind %d", kind);
+                return WK_ERR_INVALID_VALUE;
+        }
     });
 }

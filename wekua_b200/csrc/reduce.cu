@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(kRThreads) reduce_final_kernel(const typename 
 
 template <typename T, int NIN>
 static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, uint64_t rows, uint64_t run_len, uint64_t xrp,
-                           uint64_t xsp, uint64_t yrp, uint64_t ysp, void *host_out) {
+                           uint64_t xsp, uint64_t yrp, uint64_t ysp, void *host_out, void *device_out = nullptr) {
     using A = typename Acc<T>::type;
-    if (!x || (NIN == 2 && !y) || !host_out) return WK_ERR_INVALID_BUFFER;
+    if (!x || (NIN == 2 && !y) || (!host_out && !device_out)) return WK_ERR_INVALID_BUFFER;
     if (depth == 0 || rows == 0 || run_len == 0) return WK_ERR_INVALID_VALUE;
     // collapse contiguous runs
     if (rows > 1 && xrp == run_len && (NIN == 1 || yrp == run_len)) { run_len *= rows; rows = 1; }
@@ -132,7 +132,7 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     int32_t rc = ensure_scratch(q, n_part * sizeof(A) + 64);
     if (rc != WK_OK) return rc;
     A *partial = reinterpret_cast<A *>((char *)q->scratch + 64);
-    T *result = reinterpret_cast<T *>(q->scratch);
+    T *result = device_out ? reinterpret_cast<T *>(device_out) : reinterpret_cast<T *>(q->scratch);
     dim3 grid((unsigned)gx, (unsigned)gy);
     if (vec)
         reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
@@ -141,6 +141,7 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     WK_CHECK_LAUNCH();
     reduce_final_kernel<T><<<1, kRThreads, 0, q->stream>>>(partial, n_part, result);
     WK_CHECK_LAUNCH();
+    if (device_out) return WK_OK;  // async form: the scalar stays on the device, stream-ordered
     WK_CUDA(cudaMemcpyAsync(q->pinned, result, sizeof(T), cudaMemcpyDeviceToHost, q->stream));
     WK_CUDA(cudaStreamSynchronize(q->stream));
     memcpy(host_out, q->pinned, sizeof(T));
@@ -218,6 +219,26 @@ WK_API int32_t wk_dot_reduce(wk_queue *q, int32_t dtype, uint64_t depth, uint64_
     return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
         return reduce_runs<scalar_t, 2>(q, (const scalar_t *)x, (const scalar_t *)y, depth, rows, cols, xrp, xsp, yrp, ysp,
                                         host_out);
+    });
+}
+
+WK_API int32_t wk_sum_async(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t row_pitch, uint64_t slice_pitch,
+                            const void *x, void *device_out) {
+    WK_CHECK_QUEUE(q);
+    if (!device_out) return WK_ERR_INVALID_BUFFER;
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
+        return reduce_runs<scalar_t, 1>(q, (const scalar_t *)x, nullptr, depth, rows, row_pitch, row_pitch, slice_pitch, 0, 0,
+                                        nullptr, device_out);
+    });
+}
+
+WK_API int32_t wk_dot_reduce_async(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, const void *x,
+                                   uint64_t xrp, uint64_t xsp, const void *y, uint64_t yrp, uint64_t ysp, void *device_out) {
+    WK_CHECK_QUEUE(q);
+    if (!device_out) return WK_ERR_INVALID_BUFFER;
+    return WK_DISPATCH_ALL(dtype, [&]() -> int32_t {
+        return reduce_runs<scalar_t, 2>(q, (const scalar_t *)x, (const scalar_t *)y, depth, rows, cols, xrp, xsp, yrp, ysp,
+                                        nullptr, device_out);
     });
 }
 

@@ -24,7 +24,30 @@ def _params(cache):
                     yield b, bg
 
 
+_KIND = {"gd": 0, "gdm": 1, "adagrad": 2, "rmsprop": 3, "adam": 4}
+
+
+def _step_multi(pipeline, kind, records, lr, h0=None, h1=None, h2=None, t=0):
+    """wk_optimizer_step_multi: one launch for the whole parameter list instead of the reference's one
+    kernel per weight / bias tensor; bit-identical to the per-tensor calls.  records = [(x, g, state0, state1)]"""
+    if not records:
+        return
+    dtype = records[0][0].dtype
+    arr = (capi.OptParam * len(records))()
+    for i, (x, g, s0, s1) in enumerate(records):
+        if x.dtype != dtype:
+            raise capi.UnqualTensorsAttribute("UnqualTensorsAttribute: mixed dtypes in one optimizer step")
+        arr[i] = capi.OptParam(x.ptr, g.ptr, s0.ptr if s0 is not None else None, s1.ptr if s1 is not None else None,
+                               x.number_of_elements)
+    keep = [_scalar(dtype, v) for v in (lr, h0, h1, h2)]
+    capi.check(capi.lib().wk_optimizer_step_multi(pipeline.q, records[0][0].type_index, _KIND[kind], arr, len(records),
+                                                  keep[0][1], keep[1][1], keep[2][1], keep[3][1], t))
+
+
 class Optimizer:
+    #: fused = True applies the update to every parameter tensor in ONE launch; False is the reference's per-tensor loop
+    fused = True
+
     def step(self, pipeline, cache):
         raise NotImplementedError
 
@@ -59,6 +82,9 @@ class GD(Optimizer):
         return cls(lr)
 
     def step(self, pipeline, cache):
+        if self.fused:
+            # the whole padded buffer, like the reference's vectorised axpy; gradient padding is zero
+            return _step_multi(pipeline, "gd", [(x, g, None, None) for x, g in _params(cache)], self.lr)
         for x, g in _params(cache):
             blas.axpy(pipeline, g, self.lr, x)
 
@@ -68,6 +94,9 @@ class GDM(Optimizer):
         self.lr, self.beta, self._state = lr, beta, {}
 
     def step(self, pipeline, cache):
+        if self.fused:
+            recs = [(x, g, self._state_for(pipeline, x, 1)[0], None) for x, g in _params(cache)]
+            return _step_multi(pipeline, "gdm", recs, self.lr, self.beta)
         for x, g in _params(cache):
             (v,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
@@ -80,6 +109,9 @@ class Adagrad(Optimizer):
         self.lr, self._state = lr, {}
 
     def step(self, pipeline, cache):
+        if self.fused:
+            recs = [(x, g, self._state_for(pipeline, x, 1)[0], None) for x, g in _params(cache)]
+            return _step_multi(pipeline, "adagrad", recs, self.lr)
         for x, g in _params(cache):
             (h,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
@@ -91,6 +123,9 @@ class RMSProp(Optimizer):
         self.lr, self.gamma, self._state = lr, gamma, {}
 
     def step(self, pipeline, cache):
+        if self.fused:
+            recs = [(x, g, self._state_for(pipeline, x, 1)[0], None) for x, g in _params(cache)]
+            return _step_multi(pipeline, "rmsprop", recs, self.lr, self.gamma)
         for x, g in _params(cache):
             (h,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
@@ -104,6 +139,9 @@ class Adam(Optimizer):
 
     def step(self, pipeline, cache):
         self.t += 1
+        if self.fused:
+            recs = [(x, g, *self._state_for(pipeline, x, 2)) for x, g in _params(cache)]
+            return _step_multi(pipeline, "adam", recs, self.lr, self.beta1, self.beta2, self.eps, self.t)
         for x, g in _params(cache):
             m, v = self._state_for(pipeline, x, 2)
             sc = [_scalar(x.dtype, s) for s in (self.lr, self.beta1, self.beta2, self.eps)]
