@@ -241,8 +241,10 @@ def hbm_roofline(gbs, peaks, traffic=None):
             "traffic": traffic, "peak_basis": f"{peaks['_source']} copy bandwidth"}
 
 
-def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks):
-    """benchmark/axpy.zig:119-162: alternating axpy(x, a, y) / axpy(y, a, x) on N-element vectors"""
+def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks, barrier=None, reduce_max=None, world=1):
+    """benchmark/axpy.zig:119-162: alternating axpy(x, a, y) / axpy(y, a, x) on N-element vectors.  With world > 1 every
+    rank streams its OWN n-element vectors (the path shards with no exchange step: weak scaling), timed between barriers
+    as the max over ranks; value = all ranks' bytes / that time."""
     x = wk.Tensor.alloc(ctx, pipe, (n,), dtype)
     y = wk.Tensor.alloc(ctx, pipe, (n,), dtype)
     wk.tensor.random.uniform(pipe, x, 42)
@@ -259,16 +261,20 @@ def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks):
             wk.blas.axpy(pipe, y, a, x)
         state["i"] = i + 1
 
-    ms, launches, _, _ = timed(wk, pipe, step, steps, warmup)
+    ms, launches, _, _ = timed(wk, pipe, step, steps, warmup, barrier)
+    if reduce_max is not None:
+        ms = reduce_max(ms)
     bytes_per = 3.0 * n * np.dtype(dtype).itemsize
     gbs = bytes_per * steps / (ms * 1e-3) / 1e9
     x.release(pipe)
     y.release(pipe)
     name = "f32" if np.dtype(dtype) == np.float32 else "f64"
-    return {"metric": f"axpy_{name}_gbs", "value": gbs, "unit": "GB/s", "ms_per_step": ms / steps, "dtype": name,
-            "config": {"workload": f"{name} axpy, 2^{int(np.log2(n))} elements, alternating x/y (benchmark/axpy.zig)",
+    per_rank = f", per GPU x {world} GPUs" if world > 1 else ""
+    return {"metric": f"axpy_{name}_gbs", "value": gbs * world, "unit": "GB/s", "ms_per_step": ms / steps, "dtype": name,
+            "n_gpus": world, "scaling": "weak",
+            "config": {"workload": f"{name} axpy, 2^{int(np.log2(n))} elements{per_rank}, alternating x/y (benchmark/axpy.zig)",
                        "l2": "inputs_exceed_l2"},
-            "gpu_launches": launches,
+            "gpu_launches": launches * world,
             "roofline": hbm_roofline(gbs, peaks, NCU_TRAFFIC_BYTES.get(f"axpy_{name}_2^{int(np.log2(n))}"))}
 
 
@@ -493,6 +499,10 @@ def run_ours(args):
         also.append(bench_gemm_single(wk, ctx, pipe, np.float64, 16384 if not args.small else 4096, max(3, s2 // 2), 3, peaks))
         also.append(bench_axpy(wk, ctx, pipe, np.float32, 1 << 28, 50, 5, peaks))
         also.append(bench_axpy(wk, ctx, pipe, np.float64, 1 << 28, 50, 5, peaks))
+    if world > 1 and not args.quick:  # "AXPY HBM GB/s at 1/2/4/8 B200": every rank streams its own vectors
+        for dt_ in (np.float32, np.float64):
+            r_ = bench_axpy(wk, ctx, pipe, dt_, 1 << 28, 50, 5, peaks, barrier, max_over_ranks, world)
+            also.append(r_)
     if world == 1 and rank == 0 and not args.no_cpu:
         r = cpu_reference_gemm(args.ref_n, np.float32, 3, 1)
         cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["cores"], "kind": "port",

@@ -666,6 +666,19 @@ template <typename T> struct Optimizer {  // optimizers/main.zig vtable {step, z
         for (auto &s : cache->slots) s.layer->parameters(s.cache.get(), params);
         return params;
     }
+    // the whole parameter list in ONE launch (wk_optimizer_step_multi) instead of the reference's kernel per tensor;
+    // bit-identical element-wise results.  state(x, i) returns the i-th state tensor of parameter x, or nullptr.
+    template <typename StateOf>
+    static void stepMulti(Pipeline *p, Cache *cache, int kind, StateOf state, const T *lr, const T *h0 = nullptr,
+                          const T *h1 = nullptr, const T *h2 = nullptr, uint64_t t = 0) {
+        std::vector<wk_opt_param_t> recs;
+        for (auto &pg : walk(cache)) {
+            Tensor<T> *s0 = state(pg.first, 0), *s1 = state(pg.first, 1);
+            recs.push_back({pg.first->buffer, pg.second->buffer, s0 ? s0->buffer : nullptr, s1 ? s1->buffer : nullptr,
+                            pg.first->number_of_elements});
+        }
+        check(wk_optimizer_step_multi(p->q(), Tensor<T>::type_index, kind, recs.data(), (uint32_t)recs.size(), lr, h0, h1, h2, t));
+    }
 };
 
 template <typename T> struct GDConfig { T lr = (T)1; };
@@ -677,7 +690,18 @@ template <typename T> struct GD : Optimizer<T> {  // gd.zig:30-94: axpy(g, -lr, 
         return o;
     }
     void step(Pipeline *p, typename Optimizer<T>::Cache *cache) override {
-        for (auto &pg : Optimizer<T>::walk(cache)) blas::axpy<T>(p, pg.second, neg_lr, pg.first);
+        // axpy touches the LOGICAL region only: tensors whose logical region is a contiguous prefix of the buffer share
+        // one launch (wk_optimizer_step_multi), tensors with padded rows keep the pitched per-tensor kernel
+        std::vector<wk_opt_param_t> recs;
+        auto prefix = [](const Tensor<T> *t) { return t->depth == 1 && (t->rows == 1 || t->row_pitch == t->cols); };
+        for (auto &pg : Optimizer<T>::walk(cache)) {
+            if (prefix(pg.first) && prefix(pg.second))
+                recs.push_back({pg.first->buffer, pg.second->buffer, nullptr, nullptr, pg.first->rows * pg.first->cols});
+            else
+                blas::axpy<T>(p, pg.second, neg_lr, pg.first);
+        }
+        check(wk_optimizer_step_multi(p->q(), Tensor<T>::type_index, WK_OPT_GD, recs.data(), (uint32_t)recs.size(), &neg_lr, nullptr,
+                                      nullptr, nullptr, 0));
     }
 };
 
@@ -689,6 +713,9 @@ template <typename T> struct Stateful : Optimizer<T> {
             if (s.first == x) return s.second.get();
         state.push_back({x, Tensor<T>::alloc(x->context, p, x->shape)});
         return state.back().second.get();
+    }
+    auto firstState(Pipeline *p) {
+        return [this, p](Tensor<T> *x, int i) -> Tensor<T> * { return i == 0 ? stateFor(p, x) : nullptr; };
     }
     void zero(Pipeline *p) override {
         for (auto &s : state) tensor_module::fill::zeroes<T>(p, s.second.get());
@@ -707,9 +734,7 @@ template <typename T> struct GDM : Stateful<T> {  // gdm.zig + gdm.cl:3-33
         return o;
     }
     void step(Pipeline *p, typename Optimizer<T>::Cache *cache) override {
-        for (auto &pg : Optimizer<T>::walk(cache))
-            check(wk_gdm(p->q(), Tensor<T>::type_index, pg.first->buffer, pg.second->buffer, this->stateFor(p, pg.first)->buffer, &lr, &beta,
-                         pg.first->number_of_elements));
+        Optimizer<T>::stepMulti(p, cache, WK_OPT_GDM, this->firstState(p), &lr, &beta);
     }
 };
 template <typename T> struct Adagrad : Stateful<T> {  // adagrad.zig + adagrad.cl:3-48
@@ -720,9 +745,7 @@ template <typename T> struct Adagrad : Stateful<T> {  // adagrad.zig + adagrad.c
         return o;
     }
     void step(Pipeline *p, typename Optimizer<T>::Cache *cache) override {
-        for (auto &pg : Optimizer<T>::walk(cache))
-            check(wk_adagrad(p->q(), Tensor<T>::type_index, pg.first->buffer, pg.second->buffer, this->stateFor(p, pg.first)->buffer, &lr,
-                             pg.first->number_of_elements));
+        Optimizer<T>::stepMulti(p, cache, WK_OPT_ADAGRAD, this->firstState(p), &lr);
     }
 };
 template <typename T> struct RMSProp : Stateful<T> {  // rmsprop.zig:111-202 + rmsprop.cl:3-57
@@ -734,10 +757,27 @@ template <typename T> struct RMSProp : Stateful<T> {  // rmsprop.zig:111-202 + r
         return o;
     }
     void step(Pipeline *p, typename Optimizer<T>::Cache *cache) override {
-        for (auto &pg : Optimizer<T>::walk(cache))
-            check(wk_rmsprop(p->q(), Tensor<T>::type_index, pg.first->buffer, pg.second->buffer, this->stateFor(p, pg.first)->buffer, &lr,
-                             &gamma, pg.first->number_of_elements));
+        Optimizer<T>::stepMulti(p, cache, WK_OPT_RMSPROP, this->firstState(p), &lr, &gamma);
     }
+};
+// Adam: adam.zig is an empty file in the reference; textbook bias-corrected update, two state tensors
+template <typename T> struct Adam : Optimizer<T> {
+    T lr, beta1, beta2, eps;
+    uint64_t t = 0;
+    Stateful<T> m, v;
+    static std::unique_ptr<Adam> init(T lr = (T)1e-3, T beta1 = (T)0.9, T beta2 = (T)0.999, T eps = (T)1e-8) {
+        std::unique_ptr<Adam> o(new Adam());
+        o->lr = lr; o->beta1 = beta1; o->beta2 = beta2; o->eps = eps;
+        return o;
+    }
+    void step(Pipeline *p, typename Optimizer<T>::Cache *cache) override {
+        ++t;
+        Optimizer<T>::stepMulti(p, cache, WK_OPT_ADAM,
+                                [this, p](Tensor<T> *x, int i) -> Tensor<T> * { return i == 0 ? m.stateFor(p, x) : v.stateFor(p, x); },
+                                &lr, &beta1, &beta2, &eps, t);
+    }
+    void zero(Pipeline *p) override { m.zero(p); v.zero(p); t = 0; }
+    void deinit(Pipeline *p) override { m.deinit(p); v.deinit(p); }
 };
 }  // namespace optimizer_module
 }  // namespace nn

@@ -376,47 +376,50 @@ template <typename BT, bool RANGE> struct UniformF<Cx<BT>, RANGE> {
 };
 
 // bias.cl:3-19: out[i] += bias[i % row_pitch], i < n.  Flat streaming over the buffer like map_vec_kernel (128-bit
-// accesses, kUnroll vectors in flight per thread); each thread tracks the bias column of its vectors incrementally --
-// one 64-bit modulo before the loop, an add and a conditional subtract per step -- and reads bias through L1.
-// VECTOR = false is the same loop over single elements (row pitch or n not a multiple of the vector width).
+// accesses, kBiasUnroll vectors of `out` in flight per thread -- only `out` comes from DRAM, so it needs a deeper
+// unroll than the two-operand kernels to keep the same bytes in flight); each thread tracks the bias column of its
+// vectors incrementally -- one modulo before the loop, an add and a conditional subtract per step -- and reads bias
+// through L1 at the point of use.  VECTOR = false is the same loop over single elements (row pitch or n not a
+// multiple of the vector width).  rp_units < 2^32 (host-checked).
+constexpr int kBiasUnroll = 8;
 template <typename T, bool VECTOR>
-__global__ void __launch_bounds__(kThreads) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias, uint64_t rp_units,
-                                                            uint64_t n_units) {
+__global__ void __launch_bounds__(kThreads, 4) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias, uint32_t rp_units,
+                                                               uint64_t n_units) {
     constexpr int VEC = VECTOR ? 16 / (int)sizeof(T) : 1;
     union Pack { uint4 u; T e[16 / sizeof(T)]; };
-    const uint64_t chunk = (uint64_t)kThreads * kUnroll;
+    const uint64_t chunk = (uint64_t)kThreads * kBiasUnroll;
     const uint64_t step = (uint64_t)gridDim.x * chunk;
-    const uint64_t step_mod = step % rp_units;
-    uint64_t col[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; u++) col[u] = ((uint64_t)blockIdx.x * chunk + (uint64_t)u * kThreads + threadIdx.x) % rp_units;
+    const uint32_t step_mod = (uint32_t)(step % rp_units), thr_mod = (uint32_t)(kThreads % rp_units);
+    // column of this thread's first vector; the u-th vector sits u * kThreads further on
+    uint32_t col0 = (uint32_t)(((uint64_t)blockIdx.x * chunk + threadIdx.x) % rp_units);
     for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < n_units; base += step) {
-        Pack o[kUnroll], b[kUnroll];
+        Pack o[kBiasUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
+        for (int u = 0; u < kBiasUnroll; u++) {
             const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
             if (vi < n_units) {
-                if (VECTOR) {
-                    o[u].u = ld_rw(reinterpret_cast<const uint4 *>(out) + vi);
-                    b[u].u = __ldg(reinterpret_cast<const uint4 *>(bias) + col[u]);
-                } else {
-                    o[u].e[0] = out[vi];
-                    b[u].e[0] = __ldg(bias + col[u]);
-                }
+                if (VECTOR) o[u].u = ld_rw(reinterpret_cast<const uint4 *>(out) + vi);
+                else o[u].e[0] = out[vi];
             }
         }
+        uint32_t col = col0;
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
+        for (int u = 0; u < kBiasUnroll; u++) {
             const uint64_t vi = base + (uint64_t)u * kThreads + threadIdx.x;
             if (vi < n_units) {
+                Pack b;
+                if (VECTOR) b.u = __ldg(reinterpret_cast<const uint4 *>(bias) + col);
+                else b.e[0] = __ldg(bias + col);
 #pragma unroll
-                for (int e = 0; e < VEC; e++) o[u].e[e] += b[u].e[e];
+                for (int e = 0; e < VEC; e++) o[u].e[e] += b.e[e];
                 if (VECTOR) st_na(reinterpret_cast<uint4 *>(out) + vi, o[u].u);
                 else out[vi] = o[u].e[0];
             }
-            col[u] += step_mod;
-            if (col[u] >= rp_units) col[u] -= rp_units;
+            col += thr_mod;
+            if (col >= rp_units) col -= rp_units;
         }
+        col0 += step_mod;
+        if (col0 >= rp_units) col0 -= rp_units;
     }
 }
 
@@ -442,16 +445,20 @@ __global__ void __launch_bounds__(256) transpose2d_kernel(const T *__restrict__ 
     }
 }
 
-// 64 x 64 tile, 128-bit global accesses on both sides (kIter vectors in flight per thread), elements cross over through
+// 64 x 64 (64 x 32 for 8-byte elements) tile, 128-bit global accesses on both sides, elements cross over through
 // a padded shared tile with scalar accesses (2-way bank conflicts at worst, far below the HBM time of the tile).
 // Needs rows, cols and both pitches to be multiples of the vector width and 16-byte aligned pointers.
 template <typename T>
 __global__ void __launch_bounds__(256) transpose2d_vec_kernel(const T *__restrict__ src, uint64_t sp, T *__restrict__ dst,
                                                               uint64_t dp, uint64_t rows, uint64_t cols) {
-    constexpr int VEC = 16 / (int)sizeof(T), TS = 64, VPR = TS / VEC, ITER = TS * VPR / 256;
-    __shared__ T tile[TS][TS + 1];
+    // 64 rows x TC columns; 8-byte elements take 32 columns so that a block keeps the 16 KiB footprint (and the 8+
+    // resident blocks per SM) of the 4-byte case -- with 32 KiB tiles only 4 blocks fit and their load / store phases
+    // no longer overlap enough (ncu: 61 % of DRAM peak)
+    constexpr int VEC = 16 / (int)sizeof(T), TS = 64, TC = sizeof(T) == 8 ? 32 : 64, VPR = TC / VEC, ITER = TS * VPR / 256;
+    constexpr int VPC = TS / VEC, ITER_OUT = TC * VPC / 256;
+    __shared__ T tile[TS][TC + 1];
     union Pack { uint4 u; T e[VEC]; };
-    const uint64_t c0 = (uint64_t)blockIdx.x * TS, r0 = (uint64_t)blockIdx.y * TS;
+    const uint64_t c0 = (uint64_t)blockIdx.x * TC, r0 = (uint64_t)blockIdx.y * TS;
     Pack in[ITER];
 #pragma unroll
     for (int k = 0; k < ITER; k++) {
@@ -467,8 +474,8 @@ __global__ void __launch_bounds__(256) transpose2d_vec_kernel(const T *__restric
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < ITER; k++) {
-        const int v = k * 256 + threadIdx.x, c = v / VPR, rv = v % VPR;
+    for (int k = 0; k < ITER_OUT; k++) {
+        const int v = k * 256 + threadIdx.x, c = v / VPC, rv = v % VPC;
         const uint64_t gc = c0 + c, gr = r0 + (uint64_t)rv * VEC;
         if (gc < cols && gr < rows) {
             Pack o;
@@ -769,15 +776,19 @@ WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void 
         const bool vec = aligned16(output) && aligned16(bias) && row_pitch % VEC == 0 && n % VEC == 0;
         const uint64_t n_units = vec ? n / VEC : n, rp_units = vec ? row_pitch / VEC : row_pitch;
         if (n_units == 0) return WK_OK;
-        uint64_t blocks = (n_units + (uint64_t)kThreads * kUnroll - 1) / ((uint64_t)kThreads * kUnroll);
-        const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+        if (rp_units >= (1ull << 31)) {
+            set_error("bias_add: row pitch too large");
+            return WK_ERR_INVALID_VALUE;
+        }
+        uint64_t blocks = (n_units + (uint64_t)kThreads * kBiasUnroll - 1) / ((uint64_t)kThreads * kBiasUnroll);
+        const uint64_t cap = (uint64_t)q->sm_count * 4;
         if (blocks > cap) blocks = cap;
         if (vec)
             bias_add_kernel<scalar_t, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
-                                                                                         rp_units, n_units);
+                                                                                         (uint32_t)rp_units, n_units);
         else
             bias_add_kernel<scalar_t, false><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
-                                                                                          rp_units, n_units);
+                                                                                          (uint32_t)rp_units, n_units);
         WK_CHECK_LAUNCH();
         return WK_OK;
     });
@@ -878,7 +889,8 @@ WK_API int32_t wk_transpose2d(wk_queue *q, int32_t dtype, uint64_t rows, uint64_
             constexpr uint64_t VEC = 16 / sizeof(scalar_t);
             if (aligned16(src) && aligned16(dst) && rows % VEC == 0 && cols % VEC == 0 && sp % VEC == 0 && dp % VEC == 0 &&
                 (rows + 63) / 64 <= 65535) {
-                dim3 vgrid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+                constexpr uint64_t TC = sizeof(scalar_t) == 8 ? 32 : 64;
+                dim3 vgrid((unsigned)((cols + TC - 1) / TC), (unsigned)((rows + 63) / 64));
                 transpose2d_vec_kernel<scalar_t><<<vgrid, 256, 0, q->stream>>>((const scalar_t *)src, sp, (scalar_t *)dst, dp, rows,
                                                                               cols);
                 WK_CHECK_LAUNCH();

@@ -57,6 +57,13 @@ struct Params {
     int op_a, op_b;
     int split;  // 0: store hi = rna_tf32(x) explicitly; 1: leave x in place, the tensor core truncates; 2: rounds
     uint32_t tiles_m, tiles_n, group_m;
+    // split-K (small problems that cannot fill the chip with output tiles): a work item is (tile, split); every split
+    // accumulates kb_per_split k-blocks into its own TMEM accumulator, parks the raw partial tile in `ws`, counts its
+    // arrival and waits for the tile's other splits (all resident); then every split folds its share of the tile's
+    // column chunks -- partials added in split order (deterministic) -- and runs the epilogue on them.
+    uint32_t splits, kb_per_split;
+    float *ws;
+    unsigned *tickets;
     int n_peers, self;
     float *peers[16];
 };
@@ -69,6 +76,15 @@ struct Barriers {
     uint64_t acc_empty[2];            // epilogue of both CTAs -> MMA           (leader CTA's copy is used)
     uint32_t tmem_base;
 };
+
+// work item -> (tile, first k-block, end k-block)
+__device__ __forceinline__ void work_coords(const Params &p, uint32_t w, uint32_t num_kb, uint32_t &tile, uint32_t &sp, uint32_t &kb0,
+                                            uint32_t &kb1) {
+    tile = w / p.splits;
+    sp = w - tile * p.splits;
+    kb0 = sp * p.kb_per_split;
+    kb1 = min(num_kb, kb0 + p.kb_per_split);
+}
 
 __device__ __forceinline__ void tile_coords(uint32_t t, uint32_t tiles_m, uint32_t tiles_n, uint32_t GM, uint32_t &tm, uint32_t &tn) {
     // groups of GM row-tiles sweep the columns together so concurrently resident tiles share A and B panels in L2
@@ -104,7 +120,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 1 ? 0u : cluster_ctarank();
     const uint32_t unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // a unit = one CTA or one CTA pair
-    const uint32_t num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.splits;  // work items: (tile, split)
     const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
 
     if (warp == 0 && lane == 0) {
@@ -135,12 +151,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ================================================================= TMA producer (every CTA, own operand halves)
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t t = unit; t < num_tiles; t += n_units) {
-                uint32_t tm, tn;
+            for (uint32_t w = unit; w < num_tiles; w += n_units) {
+                uint32_t t, sp, kb0, kb1, tm, tn;
+                work_coords(p, w, num_kb, t, sp, kb0, kb1);
                 tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
                 const int32_t m0 = (int32_t)((tm * CTAS + rank) * BM);
                 const int32_t n0 = (int32_t)(tn * BN + rank * C::BN_LOAD);
-                for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->stage_free[s], ph ^ 1);
                     uint8_t *a_dst = smem + s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
@@ -171,12 +188,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t a_kstep = p.op_a == 0 ? 32 : 1024;  // bytes per k-step of 8
             const uint32_t b_kstep = p.op_b == 1 ? 32 : 1024;
             uint32_t it = 0, tile_i = 0;
-            for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
+            for (uint32_t w = unit; w < num_tiles; w += n_units, tile_i++) {
+                uint32_t t, sp, kb0, kb1;
+                work_coords(p, w, num_kb, t, sp, kb0, kb1);
                 const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
                 mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+                for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->conv_done[s], ph);
                     tc_fence_after();
@@ -188,11 +207,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const uint64_t dah = umma_desc(a_base, a_hi + k * a_kstep), dal = umma_desc(a_base, a_lo + k * a_kstep);
                             const uint64_t dbh = umma_desc(b_base, b_hi + k * b_kstep), dbl = umma_desc(b_base, b_lo + k * b_kstep);
                             if (CTAS == 1) {
-                                mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+                                mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb != kb0) | (k != 0));
                                 mma_tf32_ss(d_tmem, dah, dbl, idesc, 1);
                                 mma_tf32_ss(d_tmem, dah, dbh, idesc, 1);
                             } else {
-                                mma_tf32_ss_2cta(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+                                mma_tf32_ss_2cta(d_tmem, dal, dbh, idesc, (kb != kb0) | (k != 0));
                                 mma_tf32_ss_2cta(d_tmem, dah, dbl, idesc, 1);
                                 mma_tf32_ss_2cta(d_tmem, dah, dbh, idesc, 1);
                             }
@@ -200,10 +219,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         // smem stage reusable (in both CTAs) once these MMAs retire; last k-block: accumulator complete
                         if (CTAS == 1) {
                             mma_commit(&bars->stage_free[s]);
-                            if (kb == num_kb - 1) mma_commit(&bars->acc_full[acc]);
+                            if (kb == kb1 - 1) mma_commit(&bars->acc_full[acc]);
                         } else {
                             mma_commit_2cta_multicast(&bars->stage_free[s], 3);
-                            if (kb == num_kb - 1) mma_commit_2cta_multicast(&bars->acc_full[acc], 3);
+                            if (kb == kb1 - 1) mma_commit_2cta_multicast(&bars->acc_full[acc], 3);
                         }
                     }
                     __syncwarp();
@@ -215,8 +234,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int ct = threadIdx.x - 64;  // 0..255
         const int split = p.split;
         uint32_t it = 0;
-        for (uint32_t t = unit; t < num_tiles; t += n_units) {
-            for (uint32_t kb = 0; kb < num_kb; kb++, it++) {
+        for (uint32_t w = unit; w < num_tiles; w += n_units) {
+            uint32_t t, sp, kb0, kb1;
+            work_coords(p, w, num_kb, t, sp, kb0, kb1);
+            for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&bars->raw_full[s], ph);
                 float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
@@ -254,8 +275,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         float *epi = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256) + q * 32 * EPI_PITCH;
         uint32_t tile_i = 0;
         const bool vec_ok = (p.ldc % 4 == 0);
-        for (uint32_t t = unit; t < num_tiles; t += n_units, tile_i++) {
-            uint32_t tm, tn;
+        for (uint32_t w = unit; w < num_tiles; w += n_units, tile_i++) {
+            uint32_t t, sp, kb0, kb1, tm, tn;
+            work_coords(p, w, num_kb, t, sp, kb0, kb1);
             tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
             const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
             mbar_wait(&bars->acc_full[acc], acc_ph);
@@ -263,20 +285,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t row0 = (uint64_t)(tm * CTAS + rank) * BM + q * 32;
             const uint64_t col0 = (uint64_t)tn * BN;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
-                }
-                // TMEM hands every lane one ROW (32 columns); global memory wants every warp instruction to cover whole
-                // 128-byte row segments (local HBM sectors and, for the fused all-gather, NVLink packets).  Transpose the
-                // 32 x 32 chunk through a padded per-warp shared-memory tile: 16-byte writes at a 144-byte row pitch and
-                // 16-byte reads of 8 lanes per row are both conflict-free.
+
+            // r = 32 consecutive columns [c*32, c*32+32) of this lane's row -> alpha/beta/bias/activation -> C (and peers).
+            // TMEM hands every lane one ROW (32 columns); global memory wants every warp instruction to cover whole
+            // 128-byte row segments (local HBM sectors and, for the fused all-gather, NVLink packets).  Transpose the
+            // 32 x 32 chunk through a padded per-warp shared-memory tile: 16-byte writes at a 144-byte row pitch and
+            // 16-byte reads of 8 lanes per row are both conflict-free.
+            auto store_chunk = [&](const uint32_t (&r)[32], int c) {
                 float4 *my_row = reinterpret_cast<float4 *>(epi + lane * EPI_PITCH);
 #pragma unroll
                 for (int g = 0; g < 8; g++)
@@ -330,6 +345,102 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
                 __syncwarp();  // the tile is overwritten by the next chunk
+            };
+
+            if (p.splits == 1) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+                    }
+                    store_chunk(r, c);
+                }
+            } else {
+                // split-K: park this split's raw partial of this CTA's 128 x 256 block in the workspace, in register
+                // order -- float4 index ((c * 8 + g) * 128 + thread) -- so every warp access covers 512 contiguous bytes
+                // and any CTA of the tile can fold any 32-column chunk with the same (warp, lane) -> row mapping
+                const uint64_t half = (uint64_t)t * CTAS + rank;  // which 128-row block of which tile
+                const int et = q * 32 + lane;                     // 0..127: row of the block
+                constexpr uint64_t PART_F4 = (uint64_t)BM * BN / 4;
+                float4 *mine = reinterpret_cast<float4 *>(p.ws) + (half * p.splits + sp) * PART_F4 + et;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 8; g++)
+                        __stcg(mine + (c * 8 + g) * 128, make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                                     __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])));
+                }
+                // publish, count the arrival, and wait for the other splits of the tile: all of them are resident (one
+                // work item per unit, host-checked), so this is a short spin, not a scheduling dependency
+                unsigned *arrived = p.tickets + 2 * half, *done = arrived + 1;
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (threadIdx.x == (2 + CONV_WARPS) * 32) {
+                    atomicAdd(arrived, 1u);
+                    unsigned seen;
+                    long long t0 = 0;
+                    for (uint32_t spins = 0;; spins++) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrived) : "memory");
+                        if (seen >= p.splits) break;
+                        if (spins > 4096) {  // bounded like mbar_wait: a protocol bug traps instead of hanging the GPU
+                            if (t0 == 0) t0 = clock64();
+                            else if (clock64() - t0 > 6000000000LL) __trap();
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                __threadfence();
+                // every split folds its share of the 32-column chunks (c = sp, sp + splits, ...), partials added in split
+                // order 0..splits-1 whoever does it: deterministic.  Half a chunk at a time, all splits' loads in flight.
+                const float4 *part0 = reinterpret_cast<const float4 *>(p.ws) + half * p.splits * PART_F4 + et;
+#pragma unroll 1
+                for (int c = (int)sp; c < BN / 32; c += (int)p.splits) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int hc = 0; hc < 2; hc++) {
+                        float4 v[4][4];
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; s2++)
+#pragma unroll
+                            for (int g = 0; g < 4; g++)
+                                if ((uint32_t)s2 < p.splits) v[s2][g] = __ldcg(part0 + (uint64_t)s2 * PART_F4 + (c * 8 + hc * 4 + g) * 128);
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            float4 acc4 = v[0][g];
+#pragma unroll
+                            for (int s2 = 1; s2 < 4; s2++)
+                                if ((uint32_t)s2 < p.splits) {
+                                    acc4.x += v[s2][g].x; acc4.y += v[s2][g].y; acc4.z += v[s2][g].z; acc4.w += v[s2][g].w;
+                                }
+                            r[(hc * 4 + g) * 4] = __float_as_uint(acc4.x);
+                            r[(hc * 4 + g) * 4 + 1] = __float_as_uint(acc4.y);
+                            r[(hc * 4 + g) * 4 + 2] = __float_as_uint(acc4.z);
+                            r[(hc * 4 + g) * 4 + 3] = __float_as_uint(acc4.w);
+                        }
+                    }
+                    store_chunk(r, c);
+                }
+                // the last split to finish re-arms the counters for the next launch
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (threadIdx.x == (2 + CONV_WARPS) * 32) {
+                    if (atomicAdd(done, 1u) == p.splits - 1) {
+                        *arrived = 0;
+                        *done = 0;
+                    }
+                }
             }
         }
     }
@@ -396,6 +507,57 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     p.tiles_n = (uint32_t)((N + BN - 1) / BN);
     static const int gm_env = env_int("WK_GEMM_GM", 16);
     p.group_m = gm_env > 0 ? gm_env : 16;
+    // split-K when the output tiles alone leave more than half of the chip idle (small M*N, long K): at least 4
+    // k-blocks per split, at most 8 splits; WK_GEMM_SPLITK=1 disables, =n forces n
+    const uint64_t n_out_tiles = (uint64_t)p.tiles_m * p.tiles_n;
+    static bool attr_set[64] = {false};
+    if (!attr_set[q->device & 63]) {
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        attr_set[q->device & 63] = true;
+    }
+    static int max_pairs[64] = {0};  // co-resident CTA pairs (GPCs with an odd SM count strand one SM), per device
+    if (ctas == 2 && max_pairs[q->device & 63] == 0) {
+        cudaLaunchConfig_t occ{};
+        occ.gridDim = dim3(2 * (unsigned)q->sm_count);
+        occ.blockDim = dim3(THREADS);
+        occ.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+        cudaLaunchAttribute oa[1];
+        oa[0].id = cudaLaunchAttributeClusterDimension;
+        oa[0].val.clusterDim.x = 2;
+        oa[0].val.clusterDim.y = 1;
+        oa[0].val.clusterDim.z = 1;
+        occ.attrs = oa;
+        occ.numAttrs = 1;
+        int n_cl = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_cl, gemm_tf32x3_kernel<2>, &occ) != cudaSuccess || n_cl <= 0) {
+            cudaGetLastError();
+            n_cl = q->sm_count / 2 - 4;
+        }
+        max_pairs[q->device & 63] = n_cl;
+    }
+    const uint64_t units_avail = ctas == 2 ? (uint64_t)max_pairs[q->device & 63] : (uint64_t)q->sm_count;
+    const uint32_t num_kb = (uint32_t)((K + BK - 1) / BK);
+    static const int splitk_env = env_int("WK_GEMM_SPLITK", 0);
+    uint32_t splits = 1;
+    if (splitk_env > 0) splits = (uint32_t)splitk_env;
+    else if (n_out_tiles * 2 <= units_avail) splits = (uint32_t)(units_avail / n_out_tiles);
+    if (splits > 4) splits = 4;  // the fold keeps 4 splits' loads in flight per thread
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (n_out_tiles * splits > units_avail) splits = (uint32_t)(units_avail / n_out_tiles);  // co-residency of a tile's splits
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (num_kb + splits - 1) / splits;
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    p.ws = nullptr;
+    p.tickets = nullptr;
+    if (p.splits > 1) {
+        const size_t halves = (size_t)n_out_tiles * ctas;
+        const size_t ws_bytes = halves * p.splits * BM * BN * sizeof(float);
+        int32_t rc = ensure_splitk(q, ws_bytes, 2 * halves);
+        if (rc != WK_OK) return rc;
+        p.ws = (float *)q->splitk_ws;
+        p.tickets = q->splitk_tickets;
+    }
     p.n_peers = 0;
     p.self = 0;
     if (peers && peers->n > 1) {
@@ -404,31 +566,36 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         for (int i = 0; i < peers->n; i++) p.peers[i] = (float *)peers->ptrs[i];
     }
 
-    static bool attr_set[64] = {false};
-    if (!attr_set[q->device & 63]) {
-        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-        attr_set[q->device & 63] = true;
-    }
-    const uint64_t num_tiles = (uint64_t)p.tiles_m * p.tiles_n;
+    const uint64_t num_tiles = n_out_tiles * p.splits;
     const uint64_t max_units = (uint64_t)q->sm_count / ctas;
     const unsigned units = (unsigned)(num_tiles < max_units ? num_tiles : max_units);
-    if (ctas == 1) {
-        gemm_tf32x3_kernel<1><<<units, THREADS, Cfg<1>::SMEM_BYTES, q->stream>>>(tmA, tmB, p);
-    } else {
+    {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(units * 2);
+        cfg.gridDim = dim3(units * ctas);
         cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+        cfg.dynamicSmemBytes = ctas == 1 ? Cfg<1>::SMEM_BYTES : Cfg<2>::SMEM_BYTES;
         cfg.stream = q->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (ctas == 2) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            na++;
+        }
+        if (p.splits > 1) {
+            // the splits of a tile wait for each other inside the kernel: a cooperative launch makes the driver place the
+            // whole grid at once (or not at all), so that wait can never depend on a CTA that has no SM yet -- also
+            // when another queue's kernel holds part of the chip
+            attr[na].id = cudaLaunchAttributeCooperative;
+            attr[na].val.cooperative = 1;
+            na++;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2>, tmA, tmB, p));
+        cfg.numAttrs = na;
+        if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1>, tmA, tmB, p));
+        else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2>, tmA, tmB, p));
     }
     WK_CHECK_LAUNCH();
     return WK_OK;

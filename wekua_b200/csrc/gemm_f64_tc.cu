@@ -18,6 +18,8 @@
 //     mn-contiguous operand (A transposed / B not transposed): tile[k][128 + 4]
 //   epilogue straight from registers: alpha/beta/bias/activation, 16-byte stores (and peer GPUs for the fused
 //   all-gather).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wk {
@@ -48,6 +50,11 @@ struct Params {
     const double *bias;
     int act;
     uint32_t tiles_m, tiles_n;
+    // split-K (blockIdx.y = split): every split multiplies kb_per_split k-blocks, parks its accumulator fragments in
+    // `ws` and takes a ticket; the last CTA of a tile folds the partials in split order and runs the epilogue
+    uint32_t splits, kb_per_split;
+    double *ws;
+    unsigned *tickets;
     int n_peers, self;
     double *peers[16];
 };
@@ -142,7 +149,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
     uint32_t tm, tn;
     tile_coords(blockIdx.x, p.tiles_m, p.tiles_n, tm, tn);
     const uint64_t m0 = (uint64_t)tm * BM, n0 = (uint64_t)tn * BN;
-    const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
+    const uint32_t total_kb = (uint32_t)((p.K + BK - 1) / BK);
+    const uint32_t kb_first = blockIdx.y * p.kb_per_split;
+    const uint32_t num_kb = min(total_kb - kb_first, p.kb_per_split);  // k-blocks of this split, numbered from 0 below
 
     double acc[2][4][4];
 #pragma unroll
@@ -154,8 +163,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
 
     auto load_stage = [&](uint32_t kb) {
         double *sa = smem + (kb % STAGES) * STAGE_DOUBLES, *sb = sa + TILE_DOUBLES;
-        load_tile<!TA>(sa, p.A, p.lda, m0, p.M, (uint64_t)kb * BK, p.K);
-        load_tile<TB>(sb, p.B, p.ldb, n0, p.N, (uint64_t)kb * BK, p.K);
+        load_tile<!TA>(sa, p.A, p.lda, m0, p.M, (uint64_t)(kb_first + kb) * BK, p.K);
+        load_tile<TB>(sb, p.B, p.ldb, n0, p.N, (uint64_t)(kb_first + kb) * BK, p.K);
     };
 
     // full[b]: every thread's cp.async of the stage in buffer b has landed (cp.async.mbarrier.arrive.noinc, 512 arrivals)
@@ -215,6 +224,50 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_dmma_kernel(const Params p) {
         }
         __syncwarp();  // every lane's shared-memory reads of this buffer have been consumed by the MMAs above
         if (lane == 0) mbar_arrive(&empty_bar[b]);
+    }
+
+    if (p.splits > 1) {
+        // fragments are owned by the same (warp, lane) in every CTA, so the workspace keeps them in register order:
+        // ws[tile][split][pair of accumulators][thread] as double2 -> every warp store covers 512 contiguous bytes
+        __shared__ uint32_t last_flag;
+        double2 *mine = reinterpret_cast<double2 *>(p.ws) + ((uint64_t)blockIdx.x * p.splits + blockIdx.y) * (16 * THREADS) + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    __stcg(mine + ((i * 4 + j) * 2 + h) * THREADS, make_double2(acc[i][j][h * 2], acc[i][j][h * 2 + 1]));
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned old = atomicAdd(p.tickets + blockIdx.x, 1u);
+            const bool last = (old == p.splits - 1);
+            if (last) p.tickets[blockIdx.x] = 0;  // self-resetting
+            last_flag = last ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!last_flag) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[i][j][e] = 0.0;
+        const double2 *part = reinterpret_cast<const double2 *>(p.ws) + (uint64_t)blockIdx.x * p.splits * (16 * THREADS) + threadIdx.x;
+        for (uint32_t s2 = 0; s2 < p.splits; s2++, part += 16 * THREADS) {  // fixed order: independent of who is last
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const double2 v = __ldcg(part + ((i * 4 + j) * 2 + h) * THREADS);
+                        acc[i][j][h * 2] += v.x;
+                        acc[i][j][h * 2 + 1] += v.y;
+                    }
+        }
     }
 
     // ---------------------------------------------------------------- epilogue: c0,c1 = (row g, cols 2t,2t+1); c2,c3 = row g+8
@@ -308,7 +361,27 @@ int32_t gemm_f64_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         WK_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set[q->device & 63] = true;
     }
-    const unsigned grid = p.tiles_m * p.tiles_n;
+    // split-K when the tiles alone leave more than half of the SMs idle: >= 16 k-blocks (256 k) per split, <= 8 splits
+    const uint64_t n_tiles = (uint64_t)p.tiles_m * p.tiles_n;
+    const uint32_t total_kb = (uint32_t)((K + BK - 1) / BK);
+    static const char *sk_env = getenv("WK_GEMM_SPLITK");
+    uint32_t splits = 1;
+    if (sk_env && *sk_env) splits = (uint32_t)atoi(sk_env);
+    else if (n_tiles * 2 <= (uint64_t)q->sm_count) splits = (uint32_t)((uint64_t)q->sm_count / n_tiles);
+    if (splits > 8) splits = 8;
+    if (splits > total_kb / 16) splits = total_kb / 16;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (total_kb + splits - 1) / splits;
+    p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.ws = nullptr;
+    p.tickets = nullptr;
+    if (p.splits > 1) {
+        int32_t rc = ensure_splitk(q, (size_t)n_tiles * p.splits * BM * BN * sizeof(double), (size_t)n_tiles);
+        if (rc != WK_OK) return rc;
+        p.ws = (double *)q->splitk_ws;
+        p.tickets = q->splitk_tickets;
+    }
+    const dim3 grid((unsigned)n_tiles, p.splits);
     if (op_a == 0 && op_b == 0) gemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
     else if (op_a == 0 && op_b == 1) gemm_dmma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);
     else if (op_a == 1 && op_b == 0) gemm_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, q->stream>>>(p);

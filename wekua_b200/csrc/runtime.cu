@@ -55,6 +55,32 @@ int32_t ensure_workspace(wk_queue *q, size_t bytes) {
     return WK_OK;
 }
 
+int32_t ensure_splitk(wk_queue *q, size_t ws_bytes, size_t n_tickets) {
+    if (q->splitk_ws_bytes < ws_bytes) {
+        if (q->splitk_ws) {
+            WK_CUDA(cudaStreamSynchronize(q->stream));
+            WK_CUDA(cudaFree(q->splitk_ws));
+            q->splitk_ws = nullptr;
+            q->splitk_ws_bytes = 0;
+        }
+        WK_CUDA(cudaMalloc(&q->splitk_ws, ws_bytes));
+        q->splitk_ws_bytes = ws_bytes;
+    }
+    if (q->splitk_n_tickets < n_tickets) {
+        if (q->splitk_tickets) {
+            WK_CUDA(cudaStreamSynchronize(q->stream));
+            WK_CUDA(cudaFree(q->splitk_tickets));
+            q->splitk_tickets = nullptr;
+            q->splitk_n_tickets = 0;
+        }
+        const size_t n = n_tickets < 1024 ? 1024 : n_tickets;
+        WK_CUDA(cudaMalloc((void **)&q->splitk_tickets, n * sizeof(unsigned)));
+        WK_CUDA(cudaMemsetAsync(q->splitk_tickets, 0, n * sizeof(unsigned), q->stream));
+        q->splitk_n_tickets = n;
+    }
+    return WK_OK;
+}
+
 static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t adopt) {
     q->device = device;
     q->wekua_id = wekua_id;
@@ -78,6 +104,11 @@ static void queue_fini(wk_queue *q) {
     if (q->scratch) cudaFree(q->scratch);
     if (q->ws) cudaFree(q->ws);
     q->ws = nullptr;
+    if (q->splitk_ws) cudaFree(q->splitk_ws);
+    if (q->splitk_tickets) cudaFree(q->splitk_tickets);
+    q->splitk_ws = nullptr;
+    q->splitk_tickets = nullptr;
+    q->splitk_ws_bytes = q->splitk_n_tickets = 0;
     q->ws_bytes = 0;
     if (q->pinned) cudaFreeHost(q->pinned);
     if (q->owns_stream && q->stream) cudaStreamDestroy(q->stream);

@@ -29,16 +29,18 @@ _KIND = {"gd": 0, "gdm": 1, "adagrad": 2, "rmsprop": 3, "adam": 4}
 
 def _step_multi(pipeline, kind, records, lr, h0=None, h1=None, h2=None, t=0):
     """wk_optimizer_step_multi: one launch for the whole parameter list instead of the reference's one
-    kernel per weight / bias tensor; bit-identical to the per-tensor calls.  records = [(x, g, state0, state1)]"""
+    kernel per weight / bias tensor; bit-identical to the per-tensor calls.  records = [(x, g, state0, state1[, n])];
+    n defaults to the whole padded buffer (what gdm.zig / adagrad.zig / rmsprop.zig launch over)."""
     if not records:
         return
     dtype = records[0][0].dtype
     arr = (capi.OptParam * len(records))()
-    for i, (x, g, s0, s1) in enumerate(records):
+    for i, rec in enumerate(records):
+        x, g, s0, s1 = rec[:4]
         if x.dtype != dtype:
             raise capi.UnqualTensorsAttribute("UnqualTensorsAttribute: mixed dtypes in one optimizer step")
         arr[i] = capi.OptParam(x.ptr, g.ptr, s0.ptr if s0 is not None else None, s1.ptr if s1 is not None else None,
-                               x.number_of_elements)
+                               rec[4] if len(rec) > 4 else x.number_of_elements)
     keep = [_scalar(dtype, v) for v in (lr, h0, h1, h2)]
     capi.check(capi.lib().wk_optimizer_step_multi(pipeline.q, records[0][0].type_index, _KIND[kind], arr, len(records),
                                                   keep[0][1], keep[1][1], keep[2][1], keep[3][1], t))
@@ -83,8 +85,17 @@ class GD(Optimizer):
 
     def step(self, pipeline, cache):
         if self.fused:
-            # the whole padded buffer, like the reference's vectorised axpy; gradient padding is zero
-            return _step_multi(pipeline, "gd", [(x, g, None, None) for x, g in _params(cache)], self.lr)
+            # axpy touches the LOGICAL region only (axpy.cl's non-vector variant; padding of a bias gradient is not zero):
+            # tensors whose logical region is one contiguous prefix of the buffer go into the one-launch list, the
+            # rest (padded rows) keep the pitched per-tensor kernel
+            recs, rest = [], []
+            for x, g in _params(cache):
+                prefix = all(t.depth == 1 and (t.rows == 1 or t.row_pitch == t.cols) for t in (x, g))
+                (recs if prefix else rest).append((x, g, None, None, x.rows * x.cols))
+            _step_multi(pipeline, "gd", recs, self.lr)
+            for x, g, *_ in rest:
+                blas.axpy(pipeline, g, self.lr, x)
+            return
         for x, g in _params(cache):
             blas.axpy(pipeline, g, self.lr, x)
 
