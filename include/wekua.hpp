@@ -430,6 +430,7 @@ template <typename T> struct Activation {  // activation/main.zig: vtable {run, 
     virtual ~Activation() {}
     virtual void run(Pipeline *p, Tensor<T> *net_output) const = 0;
     virtual void derivative(Pipeline *p, const Tensor<T> *output, Tensor<T> *d) const = 0;
+    virtual int kind() const { return WK_ACT_NONE; }  // WK_ACT_* of the fused epilogues (0: no fused form)
     void getDerivative(Pipeline *p, const Tensor<T> *output, Tensor<T> *d) const {
         tensor_module::helpers::eqlTensors(output, d);
         derivative(p, output, d);
@@ -437,6 +438,7 @@ template <typename T> struct Activation {  // activation/main.zig: vtable {run, 
 };
 template <typename T> struct Sigmoid : Activation<T> {  // sigmoid.zig:39-137
     static std::shared_ptr<Activation<T>> init() { return std::make_shared<Sigmoid<T>>(); }
+    int kind() const override { return WK_ACT_SIGMOID; }
     void run(Pipeline *p, Tensor<T> *o) const override {
         check(wk_unary(p->q(), Tensor<T>::type_index, WK_OP_SIGMOID, o->buffer, o->number_of_elements));
     }
@@ -446,6 +448,7 @@ template <typename T> struct Sigmoid : Activation<T> {  // sigmoid.zig:39-137
 };
 template <typename T> struct Tanh : Activation<T> {  // tanh.zig:25-84
     static std::shared_ptr<Activation<T>> init() { return std::make_shared<Tanh<T>>(); }
+    int kind() const override { return WK_ACT_TANH; }
     void run(Pipeline *p, Tensor<T> *o) const override {
         check(wk_unary(p->q(), Tensor<T>::type_index, WK_OP_TANH, o->buffer, o->number_of_elements));
     }
@@ -480,13 +483,17 @@ struct ExtraParams {  // linear.zig:23-26
     uint64_t deep = 1;
     bool enable_bias = true;
     std::optional<uint64_t> seed;  // the reference seeds from the wall clock (uniform.zig:82); tests pin it
+    // fused = true: forward runs gemm + bias + activation as ONE launch (wk_gemm_bias_act) wherever the output tensor has
+    // no padding (padded outputs keep the reference's three launches, whose whole-buffer kernels define what the padding
+    // holds), and backward folds act'(output) * sensitivity into one pass (wk_act_backward)
+    bool fused = true;
 };
 
 namespace linear_module {
 template <typename T> struct Linear : Layer<T> {  // linear.zig:88-678
     Context *context;
     std::shared_ptr<activation_module::Activation<T>> activation;
-    bool bias_enabled;
+    bool bias_enabled, fused = true;
     std::vector<TensorPtr<T>> weights, bias;
 
     static std::unique_ptr<Linear> init(Context *ctx, Pipeline *p, uint64_t input, uint64_t output,
@@ -496,6 +503,7 @@ template <typename T> struct Linear : Layer<T> {  // linear.zig:88-678
         l->context = ctx;
         l->activation = acti;
         l->bias_enabled = extra.enable_bias;
+        l->fused = extra.fused;
         auto limits = [](uint64_t a, uint64_t b) { return (T)std::sqrt(6.0 / (double)(a + b)); };  // linear.zig:28-45
         for (uint64_t i = 0; i < extra.deep; i++) {
             const uint64_t in = i == 0 ? input : output;
@@ -536,6 +544,15 @@ template <typename T> struct Linear : Layer<T> {  // linear.zig:88-678
         Tensor<T> *in = input;
         for (size_t i = 0; i < weights.size(); i++) {
             Tensor<T> *out = c->outputs[i].get();
+            const bool dense = out->row_pitch == out->cols && out->rows_padded == out->rows;
+            if (fused && dense && (!activation || activation->kind() != WK_ACT_NONE)) {
+                c->forward_packed[i]->validateTensors(in, Operation::no_transpose, weights[i].get(), Operation::transpose);
+                check(wk_gemm_bias_act(p->q(), Tensor<T>::type_index, 0, 1, out->rows, out->cols, in->cols, in->buffer, in->row_pitch,
+                                       weights[i]->buffer, weights[i]->row_pitch, out->buffer, out->row_pitch,
+                                       bias_enabled ? bias[i]->buffer : nullptr, activation ? activation->kind() : WK_ACT_NONE));
+                in = out;
+                continue;
+            }
             blas::gemm<T>(p, std::nullopt, in, Operation::no_transpose, weights[i].get(), Operation::transpose, std::nullopt, out,
                           c->forward_packed[i].get());
             if (bias_enabled)  // addBias, linear.zig:424-478
@@ -552,7 +569,11 @@ template <typename T> struct Linear : Layer<T> {  // linear.zig:88-678
         Tensor<T> *output = c->outputs[index].get();
         for (;;) {
             Tensor<T> *d = c->acti_derivatives[index].get();
-            if (activation) {
+            if (activation && fused && activation->kind() != WK_ACT_NONE) {
+                tensor_module::helpers::eqlTensors<T>(output, d);
+                check(wk_act_backward(p->q(), Tensor<T>::type_index, activation->kind(), output->buffer, d->buffer, sens->buffer,
+                                      sens->number_of_elements));
+            } else if (activation) {
                 activation->getDerivative(p, output, d);
                 math::dot<T>(p, sens, d);
             }

@@ -33,7 +33,7 @@ def ev():
     return e
 
 
-def timed(fn, reps=int(os.environ.get('WK_SWEEP_REPS', 20)), warm=3, prep=None):
+def timed(fn, reps=int(os.environ.get('WK_SWEEP_REPS', 20)), warm=int(os.environ.get('WK_SWEEP_WARM', 3)), prep=None):
     """prep (re-initialise the in/out operand) runs untimed before every rep; each rep is then bracketed on its own"""
     for _ in range(warm):
         if prep:

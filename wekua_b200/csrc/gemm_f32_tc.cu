@@ -404,31 +404,40 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
                 __threadfence();
                 // every split folds its share of the 32-column chunks (c = sp, sp + splits, ...), partials added in split
-                // order 0..splits-1 whoever does it: deterministic.  Half a chunk at a time, all splits' loads in flight.
+                // order 0..splits-1 whoever does it: deterministic.  Half a chunk at a time, four splits' loads in flight.
                 const float4 *part0 = reinterpret_cast<const float4 *>(p.ws) + half * p.splits * PART_F4 + et;
 #pragma unroll 1
                 for (int c = (int)sp; c < BN / 32; c += (int)p.splits) {
                     uint32_t r[32];
 #pragma unroll
                     for (int hc = 0; hc < 2; hc++) {
-                        float4 v[4][4];
+                        float4 acc4[4];
+#pragma unroll 1
+                        for (uint32_t sb = 0; sb < p.splits; sb += 4) {  // groups of 4 splits: 16 loads in flight per thread
+                            float4 v[4][4];
 #pragma unroll
-                        for (int s2 = 0; s2 < 4; s2++)
+                            for (int s2 = 0; s2 < 4; s2++)
 #pragma unroll
-                            for (int g = 0; g < 4; g++)
-                                if ((uint32_t)s2 < p.splits) v[s2][g] = __ldcg(part0 + (uint64_t)s2 * PART_F4 + (c * 8 + hc * 4 + g) * 128);
+                                for (int g = 0; g < 4; g++)
+                                    if (sb + s2 < p.splits)
+                                        v[s2][g] = __ldcg(part0 + (uint64_t)(sb + s2) * PART_F4 + (c * 8 + hc * 4 + g) * 128);
+#pragma unroll
+                            for (int g = 0; g < 4; g++) {
+                                float4 a4 = sb == 0 ? v[0][g] : acc4[g];
+#pragma unroll
+                                for (int s2 = 0; s2 < 4; s2++)
+                                    if ((sb != 0 || s2 != 0) && sb + s2 < p.splits) {
+                                        a4.x += v[s2][g].x; a4.y += v[s2][g].y; a4.z += v[s2][g].z; a4.w += v[s2][g].w;
+                                    }
+                                acc4[g] = a4;
+                            }
+                        }
 #pragma unroll
                         for (int g = 0; g < 4; g++) {
-                            float4 acc4 = v[0][g];
-#pragma unroll
-                            for (int s2 = 1; s2 < 4; s2++)
-                                if ((uint32_t)s2 < p.splits) {
-                                    acc4.x += v[s2][g].x; acc4.y += v[s2][g].y; acc4.z += v[s2][g].z; acc4.w += v[s2][g].w;
-                                }
-                            r[(hc * 4 + g) * 4] = __float_as_uint(acc4.x);
-                            r[(hc * 4 + g) * 4 + 1] = __float_as_uint(acc4.y);
-                            r[(hc * 4 + g) * 4 + 2] = __float_as_uint(acc4.z);
-                            r[(hc * 4 + g) * 4 + 3] = __float_as_uint(acc4.w);
+                            r[(hc * 4 + g) * 4] = __float_as_uint(acc4[g].x);
+                            r[(hc * 4 + g) * 4 + 1] = __float_as_uint(acc4[g].y);
+                            r[(hc * 4 + g) * 4 + 2] = __float_as_uint(acc4[g].z);
+                            r[(hc * 4 + g) * 4 + 3] = __float_as_uint(acc4[g].w);
                         }
                     }
                     store_chunk(r, c);
@@ -542,7 +551,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     uint32_t splits = 1;
     if (splitk_env > 0) splits = (uint32_t)splitk_env;
     else if (n_out_tiles * 2 <= units_avail) splits = (uint32_t)(units_avail / n_out_tiles);
-    if (splits > 4) splits = 4;  // the fold keeps 4 splits' loads in flight per thread
+    if (splits > 8) splits = 8;
     if (splits > num_kb / 4) splits = num_kb / 4;
     if (n_out_tiles * splits > units_avail) splits = (uint32_t)(units_avail / n_out_tiles);  // co-residency of a tile's splits
     if (splits < 1) splits = 1;
@@ -584,7 +593,8 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
             attr[na].val.clusterDim.z = 1;
             na++;
         }
-        if (p.splits > 1) {
+        static const int coop_env = env_int("WK_GEMM_SPLITK_COOP", 1);  // 0: plain launch (ncu cannot replay cooperative cluster launches)
+        if (p.splits > 1 && coop_env) {
             // the splits of a tile wait for each other inside the kernel: a cooperative launch makes the driver place the
             // whole grid at once (or not at all), so that wait can never depend on a CTA that has no SM yet -- also
             // when another queue's kernel holds part of the chip

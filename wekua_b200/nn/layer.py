@@ -37,7 +37,7 @@ class Linear:
     """Linear(T).init(context, pipeline, input, output, activation, ExtraParams{deep, enable_bias}) linear.zig:88-178"""
 
     def __init__(self, context: Context, pipeline: Pipeline, n_input: int, n_output: int, acti: Activation | None = None,
-                 deep: int = 1, enable_bias: bool = True, dtype=np.float32, seed=None, fused: bool = False):
+                 deep: int = 1, enable_bias: bool = True, dtype=np.float32, seed=None, fused: bool = True):
         if n_input == 0 or n_output == 0 or deep == 0:
             raise capi.InvalidValue("InvalidValue")
         self.context, self.activation, self.bias_enabled, self.dtype, self.fused = context, acti, enable_bias, np.dtype(dtype), fused
