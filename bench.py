@@ -411,7 +411,7 @@ def run_ours(args):
     if not args.no_e2e:
         ctx3 = wk.Context.init([local_rank] * 3)
         p_mm, p_up, p_dn = (wk.Pipeline.init(q) for q in ctx3.command_queues)
-        NJ = 2 if N % 512 == 0 else 1  # column panels of B and C (dense host arrays of their own, the user's layout)
+        NJ = int(os.environ.get("WK_E2E_NJ", 2)) if N % 512 == 0 else 1  # column panels of B and C (dense host arrays of their own)
         nc = N // NJ
         ha, pa = pinned_array(wk, (rows, N), dt)
         hbs, hcs, pins = [], [], [pa]
@@ -426,7 +426,7 @@ def run_ours(args):
         for jj in range(NJ):
             for r0 in range(0, N, blk.shape[0]):
                 hbs[jj][r0:r0 + blk.shape[0]] = blk[::-1, jj * nc:(jj + 1) * nc][: min(blk.shape[0], N - r0)]
-        n_panels = max(1, min(16, rows // 1024))
+        n_panels = max(1, min(int(os.environ.get("WK_E2E_PANELS", 16)), rows // 1024))
         bounds = [rows * i // n_panels for i in range(n_panels + 1)]
         es = np.dtype(dt).itemsize
         a_pan = [wk.Tensor.wrap(ctx3, p_mm, (bounds[i + 1] - bounds[i], N), dt, a.buffer + bounds[i] * a.row_pitch * es)

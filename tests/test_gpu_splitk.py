@@ -10,7 +10,9 @@ from . import gpu_helpers as gh
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1024, 1024, 1024), (256, 512, 4096), (100, 300, 2000), (128, 256, 8192), (64, 64, 16384), (384, 1000, 1100),
-          (512, 2048, 512)]
+          (512, 2048, 512),
+          # more than one round of tiles with a small last round: only the tail tiles are split (N = 4096: 3 x 74 + 34)
+          (4096, 4096, 1024), (2304, 2304, 768)]
 
 
 @pytest.mark.parametrize("op_a", [0, 1])

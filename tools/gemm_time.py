@@ -1,4 +1,5 @@
-"""time blas.gemm at given sizes: python tools/gemm_time.py f32|f64 N [N ...]   (prints TFLOP/s, CUDA events)"""
+"""time blas.gemm at given sizes: python tools/gemm_time.py f32|f64|c64|c128 N [N ...]   (prints TFLOP/s, CUDA events;
+complex products are counted as 8*N^3 real flops = 4 real multiply-adds per complex one)"""
 import ctypes as C
 import sys
 
@@ -7,7 +8,8 @@ import numpy as np
 sys.path.insert(0, ".")
 import wekua_b200 as wk  # noqa: E402
 
-dtype = np.float32 if sys.argv[1] == "f32" else np.float64
+dtype = {"f32": np.float32, "f64": np.float64, "c64": np.complex64, "c128": np.complex128}[sys.argv[1]]
+FLOPS = 8 if sys.argv[1].startswith("c") else 2
 ctx = wk.Context.init([0])
 pipe = wk.Pipeline.init(ctx.command_queues[0])
 
@@ -33,6 +35,6 @@ for n in [int(x) for x in sys.argv[2:]]:
     wk.capi.lib().wk_event_wait(e1)
     ms = C.c_float()
     wk.capi.lib().wk_event_elapsed_ms(e0, e1, C.byref(ms))
-    print(f"N={n}: {2 * n ** 3 * reps / (ms.value * 1e-3) / 1e12:.1f} TFLOP/s ({ms.value / reps:.2f} ms)", flush=True)
+    print(f"N={n}: {FLOPS * n ** 3 * reps / (ms.value * 1e-3) / 1e12:.1f} TFLOP/s ({ms.value / reps:.2f} ms)", flush=True)
     for t in (a, b, c):
         t.release(pipe)

@@ -44,9 +44,17 @@ __device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
 
 // F: struct with  static constexpr unsigned kRead, kWrite (bit i = pointer i);
 //                 __device__ void operator()(T (&v)[NP], uint64_t idx) const   (idx = element index)
+// vectors in flight per thread and pointer: kernels that read ONE operand from DRAM (scal, unary maps, activation
+// derivatives, fill-like) need twice the depth of the two- and three-operand kernels for the same bytes in flight
+template <typename F> struct KeepShallow : std::false_type {};  // specialised below for register-hungry FP64 maps
+template <typename F> constexpr int unroll_for() {
+    return ((F::kRead & (F::kRead - 1)) == 0 && !KeepShallow<F>::value) ? 2 * kUnroll : kUnroll;  // at most one read pointer
+}
+
 template <typename T, int NP, typename F>
 __global__ void __launch_bounds__(kThreads) map_vec_kernel(Ptrs<NP> ptrs, uint64_t n, F f) {
     constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int kUnroll = unroll_for<F>();  // shadows the file-scope default
     union Pack { uint4 u; T e[VEC]; };
     const uint64_t n_vec = n / VEC;
     const uint64_t chunk = (uint64_t)kThreads * kUnroll;
@@ -153,6 +161,7 @@ static int32_t launch_map(wk_queue *q, Ptrs<NP> ptrs, uint64_t n, F f) {
     const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
     if (aligned) {
         constexpr int VEC = 16 / (int)sizeof(T);
+        constexpr int kUnroll = unroll_for<F>();
         uint64_t blocks = (n / VEC + (uint64_t)kThreads * kUnroll - 1) / ((uint64_t)kThreads * kUnroll);
         if (blocks == 0) blocks = 1;
         if (blocks > cap) blocks = cap;
@@ -243,6 +252,12 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
         else v[0] = wk_sigmoid(x);
     }
 };
+
+// f64 tan / cosh / tanh are FP64-pipe bound and register-hungry: the deeper unroll only costs occupancy there
+// (measured 0.73 -> 0.65, 0.86 -> 0.76, 0.65 -> 0.56 of the copy bandwidth), so they keep 4 vectors in flight
+template <> struct KeepShallow<UnaryF<double, WK_OP_TAN>> : std::true_type {};
+template <> struct KeepShallow<UnaryF<double, WK_OP_COSH>> : std::true_type {};
+template <> struct KeepShallow<UnaryF<double, WK_OP_TANH>> : std::true_type {};
 
 template <typename BT, int OP> struct UnaryF<Cx<BT>, OP> {  // trig.cl:5-66, complex branches
     static constexpr unsigned kRead = 1, kWrite = 1;

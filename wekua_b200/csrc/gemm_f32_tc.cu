@@ -62,6 +62,7 @@ struct Params {
     // arrival and waits for the tile's other splits (all resident); then every split folds its share of the tile's
     // column chunks -- partials added in split order (deterministic) -- and runs the epilogue on them.
     uint32_t splits, kb_per_split;
+    uint32_t n_full;  // tiles [0, n_full) are not split (whole waves); only the tail tiles [n_full, tiles) are
     float *ws;
     unsigned *tickets;
     int n_peers, self;
@@ -80,8 +81,17 @@ struct Barriers {
 // work item -> (tile, first k-block, end k-block)
 __device__ __forceinline__ void work_coords(const Params &p, uint32_t w, uint32_t num_kb, uint32_t &tile, uint32_t &sp, uint32_t &kb0,
                                             uint32_t &kb1) {
-    tile = w / p.splits;
-    sp = w - tile * p.splits;
+    if (w < p.n_full) {  // a whole tile
+        tile = w;
+        sp = 0;
+        kb0 = 0;
+        kb1 = num_kb;
+        return;
+    }
+    const uint32_t r = w - p.n_full;
+    const uint32_t q = r / p.splits;
+    tile = p.n_full + q;
+    sp = r - q * p.splits;
     kb0 = sp * p.kb_per_split;
     kb1 = min(num_kb, kb0 + p.kb_per_split);
 }
@@ -120,7 +130,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 1 ? 0u : cluster_ctarank();
     const uint32_t unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // a unit = one CTA or one CTA pair
-    const uint32_t num_tiles = p.tiles_m * p.tiles_n * p.splits;  // work items: (tile, split)
+    const uint32_t num_tiles = p.n_full + (p.tiles_m * p.tiles_n - p.n_full) * p.splits;  // work items: tiles, then (tail tile, split)
     const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
 
     if (warp == 0 && lane == 0) {
@@ -347,7 +357,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();  // the tile is overwritten by the next chunk
             };
 
-            if (p.splits == 1) {
+            if (p.splits == 1 || w < p.n_full) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {
                     uint32_t r[32];
@@ -364,7 +374,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // split-K: park this split's raw partial of this CTA's 128 x 256 block in the workspace, in register
                 // order -- float4 index ((c * 8 + g) * 128 + thread) -- so every warp access covers 512 contiguous bytes
                 // and any CTA of the tile can fold any 32-column chunk with the same (warp, lane) -> row mapping
-                const uint64_t half = (uint64_t)t * CTAS + rank;  // which 128-row block of which tile
+                const uint64_t half = (uint64_t)(t - p.n_full) * CTAS + rank;  // which 128-row block of which split tile
                 const int et = q * 32 + lane;                     // 0..127: row of the block
                 constexpr uint64_t PART_F4 = (uint64_t)BM * BN / 4;
                 float4 *mine = reinterpret_cast<float4 *>(p.ws) + (half * p.splits + sp) * PART_F4 + et;
@@ -547,26 +557,46 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     }
     const uint64_t units_avail = ctas == 2 ? (uint64_t)max_pairs[q->device & 63] : (uint64_t)q->sm_count;
     const uint32_t num_kb = (uint32_t)((K + BK - 1) / BK);
-    static const int splitk_env = env_int("WK_GEMM_SPLITK", 0);
+    static const int splitk_env = env_int("WK_GEMM_SPLITK", 0);   // 1: never split, n: force n splits (whole problem)
+    static const int tail_env = env_int("WK_GEMM_TAILSPLIT", 1);  // 0: no tail split
+    static const int debug_env = env_int("WK_DEBUG", 0);
     uint32_t splits = 1;
+    uint64_t n_full = 0;  // unsplit tiles
     if (splitk_env > 0) splits = (uint32_t)splitk_env;
     else if (n_out_tiles * 2 <= units_avail) splits = (uint32_t)(units_avail / n_out_tiles);
+    else if (tail_env && num_kb >= 16) {
+        // wave quantisation: the persistent schedule runs ceil(tiles / units) rounds; when the last round is at most half
+        // full (N = 4096: 256 tiles = 3 rounds of 74 + 34), its tiles are split along K so the round costs 1/splits
+        const uint64_t rem = n_out_tiles % units_avail;
+        if (rem > 0 && rem * 2 <= units_avail) {
+            n_full = n_out_tiles - rem;
+            splits = (uint32_t)(units_avail / rem);
+            if (splits > 4) splits = 4;
+        }
+    }
+    const uint64_t n_split_tiles = n_out_tiles - n_full;
     if (splits > 8) splits = 8;
     if (splits > num_kb / 4) splits = num_kb / 4;
-    if (n_out_tiles * splits > units_avail) splits = (uint32_t)(units_avail / n_out_tiles);  // co-residency of a tile's splits
+    if (n_split_tiles * splits > units_avail) splits = (uint32_t)(units_avail / n_split_tiles);  // co-residency of a tile's splits
     if (splits < 1) splits = 1;
     p.kb_per_split = (num_kb + splits - 1) / splits;
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    if (p.splits == 1) n_full = 0;
+    p.n_full = (uint32_t)n_full;
     p.ws = nullptr;
     p.tickets = nullptr;
     if (p.splits > 1) {
-        const size_t halves = (size_t)n_out_tiles * ctas;
+        const size_t halves = (size_t)n_split_tiles * ctas;
         const size_t ws_bytes = halves * p.splits * BM * BN * sizeof(float);
         int32_t rc = ensure_splitk(q, ws_bytes, 2 * halves);
         if (rc != WK_OK) return rc;
         p.ws = (float *)q->splitk_ws;
         p.tickets = q->splitk_tickets;
     }
+    if (debug_env)
+        fprintf(stderr, "[wk] gemm_f32_tc %llux%llux%llu ctas=%d tiles=%llu units_avail=%llu n_full=%llu splits=%u kb/split=%u\n",
+                (unsigned long long)M, (unsigned long long)N, (unsigned long long)K, ctas, (unsigned long long)n_out_tiles,
+                (unsigned long long)units_avail, (unsigned long long)n_full, p.splits, p.kb_per_split);
     p.n_peers = 0;
     p.self = 0;
     if (peers && peers->n > 1) {
@@ -575,8 +605,9 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         for (int i = 0; i < peers->n; i++) p.peers[i] = (float *)peers->ptrs[i];
     }
 
-    const uint64_t num_tiles = n_out_tiles * p.splits;
-    const uint64_t max_units = (uint64_t)q->sm_count / ctas;
+    const uint64_t num_tiles = n_full + n_split_tiles * p.splits;
+    // split launches are cooperative: the grid must be what can be resident at once
+    const uint64_t max_units = p.splits > 1 ? units_avail : (uint64_t)q->sm_count / ctas;
     const unsigned units = (unsigned)(num_tiles < max_units ? num_tiles : max_units);
     {
         cudaLaunchConfig_t cfg{};

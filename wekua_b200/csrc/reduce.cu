@@ -132,7 +132,9 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     int32_t rc = ensure_scratch(q, n_part * sizeof(A) + 64);
     if (rc != WK_OK) return rc;
     A *partial = reinterpret_cast<A *>((char *)q->scratch + 64);
-    T *result = device_out ? reinterpret_cast<T *>(device_out) : reinterpret_cast<T *>(q->scratch);
+    // blocking form: the fold kernel stores the scalar straight into the queue's pinned host word (device-addressable
+    // under UVA), so the only thing after it is the stream synchronisation the reference's mapped read implies
+    T *result = device_out ? reinterpret_cast<T *>(device_out) : reinterpret_cast<T *>(q->pinned);
     dim3 grid((unsigned)gx, (unsigned)gy);
     if (vec)
         reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
@@ -142,7 +144,6 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     reduce_final_kernel<T><<<1, kRThreads, 0, q->stream>>>(partial, n_part, result);
     WK_CHECK_LAUNCH();
     if (device_out) return WK_OK;  // async form: the scalar stays on the device, stream-ordered
-    WK_CUDA(cudaMemcpyAsync(q->pinned, result, sizeof(T), cudaMemcpyDeviceToHost, q->stream));
     WK_CUDA(cudaStreamSynchronize(q->stream));
     memcpy(host_out, q->pinned, sizeof(T));
     return WK_OK;
@@ -152,7 +153,7 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
 // order (coalesced across c); stage 2 folds the chunks in ascending order.  With one chunk the summation order
 // is exactly the reference's.
 // VECTOR: a thread owns one 128-bit group of columns (row pitch a multiple of the vector width, aligned rows) and keeps
-// 4 row vectors in flight; per column the additions are the same ones in the same order.
+// 8 row vectors in flight; per column the additions are the same ones in the same order.
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, uint64_t rp, uint64_t rows, uint64_t n_cols,
                                                      uint64_t rows_per, T *__restrict__ out, uint64_t out_pitch) {
@@ -174,10 +175,14 @@ __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, ui
         return v;
     };
     uint64_t r = r0;
-    for (; r + 4 <= r1; r += 4, p += 4 * rp) {  // 4 loads in flight, summed in order
-        const Pack a0 = load(p), a1 = load(p + rp), a2 = load(p + 2 * rp), a3 = load(p + 3 * rp);
+    for (; r + 8 <= r1; r += 8, p += 8 * rp) {  // 8 row vectors in flight, summed in row order
+        Pack a[8];
 #pragma unroll
-        for (int e = 0; e < VEC; e++) { acc[e] += a0.e[e]; acc[e] += a1.e[e]; acc[e] += a2.e[e]; acc[e] += a3.e[e]; }
+        for (int i = 0; i < 8; i++) a[i] = load(p + i * rp);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[e] += a[i].e[e];
     }
     for (; r < r1; r++, p += rp) {
         const Pack a = load(p);
@@ -190,14 +195,33 @@ __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, ui
         if (c + e < n_cols) o[e] = acc[e];
 }
 
+// Stage 2: out[c] = sum over chunks.  32 columns x 8 chunk-lanes per block: lane j adds chunks j, j+8, ... (4 loads in
+// flight), the 8 lane sums are folded in lane order through shared memory -- fixed association, so the result is the
+// same on every launch.  (One thread per column walking all chunks serially cost ~15 us for 296 chunks.)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_stage2(const T *__restrict__ part, uint64_t n_chunks, uint64_t pitch,
                                                      uint64_t n_cols, T *__restrict__ out) {
-    const uint64_t c = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c >= n_cols) return;
+    __shared__ T lane_sum[8][33];
+    const uint64_t c = (uint64_t)blockIdx.x * 32 + threadIdx.x;
+    const int j = threadIdx.y;
     T acc = (T)0;
-    for (uint64_t k = 0; k < n_chunks; k++) acc += part[k * pitch + c];
-    out[c] = acc;
+    if (c < n_cols) {
+        uint64_t k = j;
+        for (; k + 24 < n_chunks; k += 32) {
+            const T a0 = part[k * pitch + c], a1 = part[(k + 8) * pitch + c], a2 = part[(k + 16) * pitch + c],
+                    a3 = part[(k + 24) * pitch + c];
+            acc += a0; acc += a1; acc += a2; acc += a3;
+        }
+        for (; k < n_chunks; k += 8) acc += part[k * pitch + c];
+    }
+    lane_sum[j][threadIdx.x] = acc;
+    __syncthreads();
+    if (j == 0 && c < n_cols) {
+        T r = lane_sum[0][threadIdx.x];
+#pragma unroll
+        for (int i = 1; i < 8; i++) r += lane_sum[i][threadIdx.x];
+        out[c] = r;
+    }
 }
 
 }  // namespace wk
@@ -256,7 +280,14 @@ WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *
         // enough chunks to fill the machine, but never split short columns (keeps the reference's order)
         uint64_t chunks = 1;
         if (rows > 256) {
-            chunks = ((uint64_t)q->sm_count * 2048 + col_units - 1) / col_units;  // ~2048 threads per SM
+            // exactly one resident wave: (blocks that fit on an SM) x SMs, so no partial second wave trails behind
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec ? colsum_stage1<scalar_t, true> : colsum_stage1<scalar_t, false>,
+                                                              256, 0) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 4;
+            }
+            chunks = ((uint64_t)q->sm_count * per_sm) / gx;
             const uint64_t max_chunks = (rows + 63) / 64;
             if (chunks > max_chunks) chunks = max_chunks;
             if (chunks > 65535) chunks = 65535;
@@ -279,7 +310,7 @@ WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *
         if (rc != WK_OK) return rc;
         stage1((scalar_t *)q->scratch, n_cols);
         WK_CHECK_LAUNCH();
-        colsum_stage2<scalar_t><<<(unsigned)((n_cols + 255) / 256), 256, 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
+        colsum_stage2<scalar_t><<<(unsigned)((n_cols + 31) / 32), dim3(32, 8), 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
                                                                     (scalar_t *)bias_grad);
         WK_CHECK_LAUNCH();
         return WK_OK;
