@@ -88,3 +88,36 @@ def test_splitk_fused_linear_forward(act):
     np.testing.assert_allclose(gh.to_np(y), want, rtol=0, atol=(8 * n_in + 64) * np.finfo(np.float32).eps)
     for t in (x, w, b, y):
         t.release(pipe)
+
+
+def test_splitk_graph_survives_workspace_growth():
+    """a captured split-K GEMM keeps the address of its partial-tile workspace in the graph; a larger problem that grows
+    the workspace afterwards must retire the old buffer, not free it under the graph"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(3)
+    dt = np.float32
+
+    def make(M, N, K):
+        ad, bd = rng.uniform(-1, 1, (M, K)).astype(dt), rng.uniform(-1, 1, (K, N)).astype(dt)
+        a, b, c = (wk.Tensor.alloc(ctx, pipe, s, dt) for s in ((M, K), (K, N), (M, N)))
+        wk.tensor.memory.read_from_buffer(pipe, a, ad)
+        wk.tensor.memory.read_from_buffer(pipe, b, bd)
+        return ad, bd, a, b, c
+
+    ad, bd, a, b, c = make(256, 256, 2048)
+    wk.blas.gemm(pipe, None, a, 0, b, 0, None, c)  # warm-up outside the capture
+    first = gh.to_np(c)
+    pipe.begin_capture()
+    wk.blas.gemm(pipe, None, a, 0, b, 0, None, c)
+    graph = pipe.end_capture()
+    ad2, bd2, a2, b2, c2 = make(1024, 1536, 4096)   # 4 x 6 = 24 tiles x 3 splits: a much larger workspace
+    wk.blas.gemm(pipe, None, a2, 0, b2, 0, None, c2)
+    big = gh.to_np(c2)
+    assert np.allclose(big, ad2.astype(np.float64) @ bd2.astype(np.float64), rtol=0, atol=4096 * 8 * np.finfo(dt).eps * 4)
+    wk.capi.check(wk.capi.lib().wk_memset_zero(pipe.q, c.ptr, c.size))
+    graph.launch(pipe)
+    np.testing.assert_array_equal(gh.to_np(c), first)
+    graph.release()
+    for t in (a, b, c, a2, b2, c2):
+        t.release(pipe)

@@ -28,55 +28,51 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return WK_ERR_CUDA;
 }
 
+// Replace *buf by an allocation of want_bytes.  Outside of graphs: drain the stream, free the old one.  While capturing,
+// or once this queue has captured a graph (its nodes keep the old address): retire the old buffer instead.
+int32_t grow_buffer(wk_queue *q, void **buf, size_t *cur_bytes, size_t want_bytes) {
+    if (*buf) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(q->stream, &st);
+        if (st != cudaStreamCaptureStatusNone) q->ever_captured = true;
+        if (q->ever_captured && q->n_retired < 64) {
+            q->retired[q->n_retired++] = *buf;
+        } else {
+            WK_CUDA(cudaStreamSynchronize(q->stream));
+            WK_CUDA(cudaFree(*buf));
+        }
+        *buf = nullptr;
+        *cur_bytes = 0;
+    }
+    WK_CUDA(cudaMalloc(buf, want_bytes));
+    *cur_bytes = want_bytes;
+    return WK_OK;
+}
+
 int32_t ensure_scratch(wk_queue *q, size_t bytes) {
     if (q->scratch_bytes >= bytes) return WK_OK;
-    if (q->scratch) {
-        WK_CUDA(cudaStreamSynchronize(q->stream));
-        WK_CUDA(cudaFree(q->scratch));
-        q->scratch = nullptr;
-        q->scratch_bytes = 0;
-    }
-    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
-    WK_CUDA(cudaMalloc(&q->scratch, want));
-    q->scratch_bytes = want;
-    return WK_OK;
+    return grow_buffer(q, &q->scratch, &q->scratch_bytes, bytes < (1u << 20) ? (1u << 20) : bytes);
 }
 
 int32_t ensure_workspace(wk_queue *q, size_t bytes) {
     if (q->ws_bytes >= bytes) return WK_OK;
-    if (q->ws) {
-        WK_CUDA(cudaStreamSynchronize(q->stream));
-        WK_CUDA(cudaFree(q->ws));
-        q->ws = nullptr;
-        q->ws_bytes = 0;
-    }
-    WK_CUDA(cudaMalloc(&q->ws, bytes));
-    q->ws_bytes = bytes;
-    return WK_OK;
+    return grow_buffer(q, &q->ws, &q->ws_bytes, bytes);
 }
 
 int32_t ensure_splitk(wk_queue *q, size_t ws_bytes, size_t n_tickets) {
     if (q->splitk_ws_bytes < ws_bytes) {
-        if (q->splitk_ws) {
-            WK_CUDA(cudaStreamSynchronize(q->stream));
-            WK_CUDA(cudaFree(q->splitk_ws));
-            q->splitk_ws = nullptr;
-            q->splitk_ws_bytes = 0;
-        }
-        WK_CUDA(cudaMalloc(&q->splitk_ws, ws_bytes));
-        q->splitk_ws_bytes = ws_bytes;
+        int32_t rc = grow_buffer(q, &q->splitk_ws, &q->splitk_ws_bytes, ws_bytes);
+        if (rc != WK_OK) return rc;
     }
     if (q->splitk_n_tickets < n_tickets) {
-        if (q->splitk_tickets) {
-            WK_CUDA(cudaStreamSynchronize(q->stream));
-            WK_CUDA(cudaFree(q->splitk_tickets));
-            q->splitk_tickets = nullptr;
-            q->splitk_n_tickets = 0;
-        }
-        const size_t n = n_tickets < 1024 ? 1024 : n_tickets;
-        WK_CUDA(cudaMalloc((void **)&q->splitk_tickets, n * sizeof(unsigned)));
+        const size_t n = n_tickets < 4096 ? 4096 : n_tickets;
+        size_t cur = q->splitk_n_tickets * sizeof(unsigned);
+        void *t = q->splitk_tickets;
+        int32_t rc = grow_buffer(q, &t, &cur, n * sizeof(unsigned));
+        q->splitk_tickets = (unsigned *)t;
+        q->splitk_n_tickets = rc == WK_OK ? n : 0;
+        if (rc != WK_OK) return rc;
         WK_CUDA(cudaMemsetAsync(q->splitk_tickets, 0, n * sizeof(unsigned), q->stream));
-        q->splitk_n_tickets = n;
     }
     return WK_OK;
 }
@@ -104,6 +100,8 @@ static void queue_fini(wk_queue *q) {
     if (q->scratch) cudaFree(q->scratch);
     if (q->ws) cudaFree(q->ws);
     q->ws = nullptr;
+    for (int i = 0; i < q->n_retired; i++) cudaFree(q->retired[i]);
+    q->n_retired = 0;
     if (q->splitk_ws) cudaFree(q->splitk_ws);
     if (q->splitk_tickets) cudaFree(q->splitk_tickets);
     q->splitk_ws = nullptr;
@@ -331,6 +329,7 @@ struct wk_graph {
 WK_API int32_t wk_graph_begin_capture(wk_queue *q) {
     WK_CHECK_QUEUE(q);
     WK_CUDA(cudaStreamBeginCapture(q->stream, cudaStreamCaptureModeRelaxed));
+    q->ever_captured = true;
     return WK_OK;
 }
 
