@@ -408,7 +408,87 @@ def run_ours(args):
     # (core/context.zig:145-178, pipeline.zig:35-45): queue 1 uploads B then row panels of A, queue 0 multiplies each
     # panel as soon as its upload event fires, queue 2 downloads each finished panel of C.
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world > 1:
+        # N > 1: B is the same matrix in every process's host memory, so each rank uploads only its 1/g share of B's rows
+        # over PCIe and pushes it into the peers' B over NVLink (rowshard.ReplicatedOperand) while its row panels of A
+        # follow on the upload queue; host-side barriers (a gloo group: no device synchronisation) fence "every share has
+        # landed everywhere" and "everybody has finished reading B" around the products.
+        gloo = torch.distributed.new_group(backend="gloo")
+        hostbar = lambda: torch.distributed.barrier(group=gloo)
+        ctx4 = wk.Context.init([local_rank] * 4)
+        p_mm, p_up, p_dn, p_push = (wk.Pipeline.init(q) for q in ctx4.command_queues)
+        rep = rowshard.ReplicatedOperand(ctx4, p_mm, b, rank, world)
+        ha, pa = pinned_array(wk, (rows, N), dt)
+        hb, pb = pinned_array(wk, (rep.rows, N), dt)
+        hc, pc = pinned_array(wk, (rows, N), dt)
+        pins = [pa, pb, pc]
+        P = 512
+        blk = np.random.default_rng(7).uniform(-1, 1, (P, N)).astype(dt)  # A rows repeat blk, B rows repeat blk reversed
+        for r0 in range(0, rows, P):
+            ha[r0:r0 + P] = blk[: min(P, rows - r0)]
+        brev = blk[::-1]
+        for r0 in range(0, rep.rows, P):  # global row r of B is brev[r % P]
+            idx = (rep.row0 + r0 + np.arange(min(P, rep.rows - r0))) % P
+            hb[r0:r0 + len(idx)] = brev[idx]
+        n_panels = max(1, min(int(os.environ.get("WK_E2E_PANELS", 8)), rows // 1024))
+        bounds = [rows * i // n_panels for i in range(n_panels + 1)]
+        es = np.dtype(dt).itemsize
+        a_pan = [wk.Tensor.wrap(ctx4, p_mm, (bounds[i + 1] - bounds[i], N), dt, a.buffer + bounds[i] * a.row_pitch * es)
+                 for i in range(n_panels)]
+        c_pan = [wk.Tensor.wrap(ctx4, p_mm, (bounds[i + 1] - bounds[i], N), dt, c_blk.buffer + bounds[i] * c_blk.row_pitch * es)
+                 for i in range(n_panels)]
+        rfb, wtb = wk.tensor.memory.read_from_buffer, wk.tensor.memory.write_to_buffer
+
+        def e2e_step():
+            p_mm.wait_and_cleanup()  # my products of the previous step have read B ...
+            hostbar()                # ... and so have everybody else's: B may be overwritten
+            rep.upload_share(p_up, hb)
+            p_push.wait_for(p_up.record_event())
+            rep.push_share(p_push)
+            evs = []
+            for i in range(n_panels):
+                rfb(p_up, a_pan[i], ha[bounds[i]:bounds[i + 1]])
+                evs.append(p_up.record_event())
+            p_push.wait_and_cleanup()  # my share is in every peer's B ...
+            hostbar()                  # ... and every peer's share is in mine
+            for i in range(n_panels):
+                p_mm.wait_for(evs[i])
+                wk.blas.gemm(p_mm, None, a_pan[i], 0, b, 0, None, c_pan[i])
+                p_dn.wait_for(p_mm.record_event())
+                wtb(p_dn, c_pan[i], hc[bounds[i]:bounds[i + 1]].reshape(-1))
+            p_mm.wait_for(p_dn.record_event())  # the step ends when the last panel of C is on the host
+            p_up.wait_for(p_mm.record_event())
+
+        class _All4:
+            command_queue = p_mm.command_queue
+            q = p_mm.q
+
+            @staticmethod
+            def wait_and_cleanup():
+                for p_ in (p_up, p_push, p_mm, p_dn):
+                    p_.wait_and_cleanup()
+
+        e_steps = max(1, min(args.steps, 3))
+        ems, _, _, _ = timed(wk, _All4, e2e_step, e_steps, 1, barrier)
+        ems = max_over_ranks(ems)
+        for (i_, j_) in ((0, 0), (rows - 1, N - 1), (rows // 2, 17)):  # the product did reach the host
+            bcol = np.tile(brev[:, j_].astype(np.float64), (N + P - 1) // P)[:N]
+            want = float(ha[i_].astype(np.float64) @ bcol)
+            got_ = float(hc[i_, j_])
+            assert abs(got_ - want) <= 1e-3 * max(1.0, abs(want)), (rank, i_, j_, got_, want)
+        e2e = {"value": flops * e_steps / (ems * 1e-3) / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(2 * N * N * 4), "d2h_bytes_per_step": int(N * N * 4),
+               "nvlink_bytes_per_step": int((g - 1) * N * N * 4),
+               "steps": e_steps, "ms_per_step": ems / e_steps,
+               "how": (f"per rank, 4 queues on its device: upload 1/{g} of B's rows from pinned host memory, push that share to "
+                       f"the {g - 1} peers over NVLink (IPC-mapped copies), upload {n_panels} row panels of its A block, host "
+                       "barrier, multiply panel by panel, download each finished panel of C")}
+        barrier()
+        rep.release(p_mm)
+        for p in pins:
+            wk.capi.lib().wk_host_free(p)
+        ctx4.deinit()
+    elif not args.no_e2e:
         ctx3 = wk.Context.init([local_rank] * 3)
         p_mm, p_up, p_dn = (wk.Pipeline.init(q) for q in ctx3.command_queues)
         NJ = int(os.environ.get("WK_E2E_NJ", 2)) if N % 512 == 0 else 1  # column panels of B and C (dense host arrays of their own)
@@ -539,7 +619,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=32768)
-    ap.add_argument("--ref-n", type=int, default=4096, dest="ref_n")
+    ap.add_argument("--ref-n", type=int, default=8192, dest="ref_n")
     ap.add_argument("--gather", default="fused", choices=["none", "nccl", "fused"])
     ap.add_argument("--quick", action="store_true", help="headline line only (no secondary configs)")
     ap.add_argument("--small", action="store_true")

@@ -79,3 +79,40 @@ def test_transpose2d_exact(dtype, shape):
     assert not pad[b.rows:, :].any() and not pad[:, b.cols:].any()
     for t in (a, b):
         t.release(pipe)
+
+
+@pytest.mark.parametrize("op", ["tanh", "sigmoid"])
+def test_f64_activation_accuracy_and_special_values(op):
+    """the branch-free f64 tanh / sigmoid (csrc/common.cuh) against numpy's libm over the whole range: a few ulp
+    relative (the reference tests to 1e-5 absolute, trig.zig:129-446), exact limits, NaN kept, tiny arguments not
+    lost to cancellation"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(17)
+    x = np.concatenate([
+        rng.uniform(-1.5, 1.5, 20000), rng.uniform(-25, 25, 20000), rng.uniform(-760, 760, 20000),
+        rng.uniform(0, 1, 20000) * 2.0 ** -rng.integers(0, 60, 20000) * rng.choice([-1.0, 1.0], 20000),
+        [0.0, -0.0, 1e-300, -1e-300, 19.9, 20.0, 20.1, 40.0, -40.0, 700.0, -700.0, 709.0, -745.0, 1e308, -1e308,
+         np.inf, -np.inf, np.nan],
+    ])
+    x = np.resize(x, (len(x) // 2 * 2,)).reshape(2, -1)
+    t = wk.Tensor.alloc(ctx, pipe, x.shape, np.float64)
+    wk.tensor.memory.read_from_buffer(pipe, t, x)
+    if op == "tanh":
+        wk.math.tanh(pipe, t)
+        want = np.tanh(x.astype(np.longdouble)).astype(np.float64)
+    else:
+        wk.nn.Sigmoid.init().run(pipe, t)
+        with np.errstate(over="ignore"):
+            want = (1.0 / (1.0 + np.exp(-x.astype(np.longdouble)))).astype(np.float64)
+    got = gh.to_np(t)
+    t.release(pipe)
+    finite = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(x))
+    big = finite & (np.abs(want) > 1e-290)
+    rel = np.abs(got[big] - want[big]) / np.abs(want[big])
+    assert rel.max() <= 4 * np.finfo(np.float64).eps, rel.max()
+    assert np.all(np.abs(got[finite & ~big]) <= 1e-290)
+    if op == "tanh":
+        assert np.array_equal(np.signbit(got[~np.isnan(x)]), np.signbit(x[~np.isnan(x)]))
+        assert got[x == np.inf][0] == 1.0 and got[x == -np.inf][0] == -1.0

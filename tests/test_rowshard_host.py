@@ -82,6 +82,19 @@ def _worker(rank, world, port, q):
         row0, rows = rs.shard_rows(m, world, rank)
         parts = rs.exchange(a[row0:row0 + rows] @ b, world)
         ok &= np.array_equal(np.concatenate(parts, axis=0), a @ b)
+        # replicated operand from host memory: every rank contributes only its byte span of B; the spans tile the stored
+        # buffer (padded pitch included) and writing every rank's span at its offset reassembles B on every rank
+        pitch, es = 10, 8
+        stored = np.zeros((16, pitch))
+        stored[:, :8] = b
+        flat = stored.reshape(-1).view(np.uint8)
+        row0_b, rows_b, off, nbytes = rs.share_span(16, pitch, es, world, rank)
+        spans = rs.exchange((off, nbytes, bytes(flat[off:off + nbytes])), world)
+        mine = np.zeros_like(flat)
+        for o_, n_, data in spans:
+            mine[o_:o_ + n_] = np.frombuffer(data, dtype=np.uint8)
+        ok &= spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        ok &= spans[-1][0] + spans[-1][1] == flat.size and np.array_equal(mine, flat)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -236,8 +236,12 @@ template <typename T> struct FillF {  // fill.cl:11-16
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const { v[0] = value; }
 };
 
+__device__ __forceinline__ float wk_cosh(float x) { return coshf(x); }
+__device__ __forceinline__ double wk_cosh(double x) { return wk_cosh_f64(x); }
+__device__ __forceinline__ float wk_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ double wk_tanh(double x) { return wk_tanh_f64(x); }
 __device__ __forceinline__ float wk_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ double wk_sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double wk_sigmoid(double x) { return wk_sigmoid_f64(x); }
 
 template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
     static constexpr unsigned kRead = 1, kWrite = 1;
@@ -247,17 +251,16 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
         else if (OP == WK_OP_COS) v[0] = cos(x);
         else if (OP == WK_OP_TAN) v[0] = tan(x);
         else if (OP == WK_OP_SINH) v[0] = sinh(x);
-        else if (OP == WK_OP_COSH) v[0] = cosh(x);
-        else if (OP == WK_OP_TANH) v[0] = tanh(x);
+        else if (OP == WK_OP_COSH) v[0] = wk_cosh(x);
+        else if (OP == WK_OP_TANH) v[0] = wk_tanh(x);
         else v[0] = wk_sigmoid(x);
     }
 };
 
-// f64 tan / cosh / tanh are FP64-pipe bound and register-hungry: the deeper unroll only costs occupancy there
-// (measured 0.73 -> 0.65, 0.86 -> 0.76, 0.65 -> 0.56 of the copy bandwidth), so they keep 4 vectors in flight
+// libdevice's f64 tan is issue-bound and register-hungry: the deeper unroll only costs occupancy there (measured
+// 0.73 -> 0.65 of the copy bandwidth), so it keeps 4 vectors in flight.  (f64 tanh / cosh / sigmoid were in the same
+// position until they got the branch-free constant-bank implementations of common.cuh: 0.65 / 0.86 / 0.84 -> 0.92+.)
 template <> struct KeepShallow<UnaryF<double, WK_OP_TAN>> : std::true_type {};
-template <> struct KeepShallow<UnaryF<double, WK_OP_COSH>> : std::true_type {};
-template <> struct KeepShallow<UnaryF<double, WK_OP_TANH>> : std::true_type {};
 
 template <typename BT, int OP> struct UnaryF<Cx<BT>, OP> {  // trig.cl:5-66, complex branches
     static constexpr unsigned kRead = 1, kWrite = 1;

@@ -97,8 +97,8 @@ __device__ __forceinline__ void dmma_m16n8k4(double (&c)[4], double a0, double a
 }
 
 __device__ __forceinline__ double apply_act(double v, int act) {
-    if (act == WK_ACT_SIGMOID) return 1.0 / (1.0 + exp(-v));
-    if (act == WK_ACT_TANH) return tanh(v);
+    if (act == WK_ACT_SIGMOID) return wk_sigmoid_f64(v);
+    if (act == WK_ACT_TANH) return wk_tanh_f64(v);
     return v;
 }
 

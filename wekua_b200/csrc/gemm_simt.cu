@@ -19,8 +19,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 __device__ __forceinline__ double act_apply(double v, int act) {
-    if (act == WK_ACT_SIGMOID) return 1.0 / (1.0 + exp(-v));
-    if (act == WK_ACT_TANH) return tanh(v);
+    if (act == WK_ACT_SIGMOID) return wk_sigmoid_f64(v);
+    if (act == WK_ACT_TANH) return wk_tanh_f64(v);
     return v;
 }
 template <typename A> __device__ __forceinline__ A act_apply(A v, int) { return v; }

@@ -44,13 +44,19 @@ template <typename A> __device__ __forceinline__ A block_reduce_sum(A v) {
     return r;  // valid in thread 0
 }
 
+template <typename A> __device__ __forceinline__ A ld_cg_acc(const A *p) { return __ldcg(p); }  // L2: written by other SMs
+template <typename AB> __device__ __forceinline__ CxAcc<AB> ld_cg_acc(const CxAcc<AB> *p) {
+    return CxAcc<AB>{__ldcg(&p->re), __ldcg(&p->im)};
+}
+
 // Runs: n_runs contiguous runs of run_len elements; run r starts at (r / rows) * sp + (r % rows) * rp.
 // NIN = 1: sum of x; NIN = 2: sum of x*y (y has its own pitches).
 template <typename T, int NIN, bool VECTOR>
 __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restrict__ x, const T *__restrict__ y,
                                                                 uint64_t run_len, uint64_t n_runs, uint64_t rows,
                                                                 uint64_t xrp, uint64_t xsp, uint64_t yrp, uint64_t ysp,
-                                                                typename Acc<T>::type *__restrict__ partial) {
+                                                                typename Acc<T>::type *partial, unsigned *ticket,
+                                                                T *__restrict__ out) {
     using A = typename Acc<T>::type;
     constexpr int VEC = 16 / (int)sizeof(T);
     union Pack { uint4 u; T e[VEC]; };
@@ -94,17 +100,25 @@ __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restr
     }
     A v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     v = block_reduce_sum<A>(v);
-    if (threadIdx.x == 0) partial[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kRThreads) reduce_final_kernel(const typename Acc<T>::type *__restrict__ partial,
-                                                                 uint64_t n, T *__restrict__ out) {
-    using A = typename Acc<T>::type;
-    A v = AccZero<A>::get();
-    for (uint64_t i = threadIdx.x; i < n; i += kRThreads) v = v + partial[i];
-    v = block_reduce_sum<A>(v);
-    if (threadIdx.x == 0) *out = from_acc<T>(v);
+    // One launch: the block that arrives last folds the partials -- in index order, by the same thread/shuffle tree whoever
+    // it is, so the sum does not depend on which block that was -- and re-arms the ticket for the next launch.
+    __shared__ bool is_last;
+    const unsigned n_part = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) {
+        partial[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == n_part - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    A f = AccZero<A>::get();
+    for (unsigned i = threadIdx.x; i < n_part; i += kRThreads) f = f + ld_cg_acc(partial + i);
+    f = block_reduce_sum<A>(f);
+    if (threadIdx.x == 0) {
+        *out = from_acc<T>(f);
+        *ticket = 0;
+    }
 }
 
 template <typename T, int NIN>
@@ -137,11 +151,11 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     T *result = device_out ? reinterpret_cast<T *>(device_out) : reinterpret_cast<T *>(q->pinned);
     dim3 grid((unsigned)gx, (unsigned)gy);
     if (vec)
-        reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
+        reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial,
+                                                                           q->reduce_ticket, result);
     else
-        reduce_runs_kernel<T, NIN, false><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial);
-    WK_CHECK_LAUNCH();
-    reduce_final_kernel<T><<<1, kRThreads, 0, q->stream>>>(partial, n_part, result);
+        reduce_runs_kernel<T, NIN, false><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial,
+                                                                            q->reduce_ticket, result);
     WK_CHECK_LAUNCH();
     if (device_out) return WK_OK;  // async form: the scalar stays on the device, stream-ordered
     WK_CUDA(cudaStreamSynchronize(q->stream));

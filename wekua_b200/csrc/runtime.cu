@@ -92,6 +92,8 @@ static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t ad
         q->owns_stream = true;
     }
     WK_CUDA(cudaMallocHost(&q->pinned, 256));
+    WK_CUDA(cudaMalloc((void **)&q->reduce_ticket, 64));
+    WK_CUDA(cudaMemset(q->reduce_ticket, 0, 64));
     return WK_OK;
 }
 
@@ -109,6 +111,8 @@ static void queue_fini(wk_queue *q) {
     q->splitk_ws_bytes = q->splitk_n_tickets = 0;
     q->ws_bytes = 0;
     if (q->pinned) cudaFreeHost(q->pinned);
+    if (q->reduce_ticket) cudaFree(q->reduce_ticket);
+    q->reduce_ticket = nullptr;
     if (q->owns_stream && q->stream) cudaStreamDestroy(q->stream);
     q->scratch = nullptr;
     q->pinned = nullptr;

@@ -50,6 +50,77 @@ def exchange(obj, world: int, all_gather_object=None) -> list:
     return out
 
 
+def share_span(rows_total: int, row_pitch: int, itemsize: int, world: int, rank: int) -> tuple[int, int, int, int]:
+    """(row0, rows, byte offset, bytes) of the rank's share of a replicated row-major operand: contiguous row blocks
+    that tile the stored buffer exactly (same partition law as shard_rows)"""
+    row0, rows = shard_rows(rows_total, world, rank)
+    return row0, rows, row0 * row_pitch * itemsize, rows * row_pitch * itemsize
+
+
+def map_on_peers(pipeline, t: Tensor, rank: int, world: int, all_gather_object=None):
+    """(device pointer of every rank's copy of `t` as seen from this rank, the list of mappings to close): the ranks
+    exchange CUDA-IPC handles of their own buffer and open the peers'"""
+    lib = capi.lib()
+    opened = []
+    ptrs = (C.c_void_p * world)()
+    if world == 1:
+        ptrs[0] = t.buffer
+        return ptrs, opened
+    handle = (C.c_ubyte * 64)()
+    capi.check(lib.wk_ipc_get_handle(pipeline.q, t.ptr, handle))
+    handles = exchange(bytes(handle), world, all_gather_object)
+    for r, h in enumerate(handles):
+        if r == rank:
+            ptrs[r] = t.buffer
+            continue
+        buf = (C.c_ubyte * 64).from_buffer_copy(h)
+        p = C.c_void_p()
+        capi.check(lib.wk_ipc_open_handle(pipeline.q, buf, C.byref(p)))
+        ptrs[r] = p.value
+        opened.append(p)
+    return ptrs, opened
+
+
+class ReplicatedOperand:
+    """B of the row-sharded product: every rank holds all of it in HBM, but when it comes from HOST memory (identical
+    in every process) each rank uploads only its 1/world share of the stored rows over PCIe and pushes that share into
+    the peers' buffers over NVLink (copy engines, CUDA-IPC mapped pointers) -- world x less host traffic than every
+    rank uploading the whole matrix.  The caller orders the steps: `upload_share` on an upload queue, `push_share`
+    on a queue that waits for it, then a host-side barrier after the push queue has drained (every share has landed
+    everywhere) before the product reads B, and another one before the next upload overwrites it."""
+
+    def __init__(self, context, pipeline, b: Tensor, rank: int, world: int, all_gather_object=None):
+        self.context, self.b, self.rank, self.world = context, b, rank, world
+        self.row0, self.rows, self.offset_bytes, self.share_bytes = share_span(b.shape[0], b.row_pitch, b.dtype.itemsize,
+                                                                               world, rank)
+        pipeline.wait_and_cleanup()
+        self.peer_ptrs, self._opened = map_on_peers(pipeline, b, rank, world, all_gather_object)
+        self.share = Tensor.wrap(context, pipeline, (self.rows, b.shape[1]), b.dtype, b.buffer + self.offset_bytes,
+                                 row_pitch=b.row_pitch)
+
+    def upload_share(self, pipeline, host_rows: np.ndarray) -> None:
+        """host_rows: this rank's rows [row0, row0 + rows) of B, dense"""
+        from .tensor import memory
+
+        if host_rows.shape != (self.rows, self.b.shape[1]):
+            raise capi.InvalidValue("InvalidValue: host share does not match the rank's rows of B")
+        memory.read_from_buffer(pipeline, self.share, host_rows)
+
+    def push_share(self, pipeline) -> None:
+        """copy this rank's share into every peer's B at the same offset (NVLink, one copy per peer, rotated so that
+        the ranks do not all target the same peer first)"""
+        for i in range(1, self.world):
+            r = (self.rank + i) % self.world
+            capi.check(capi.lib().wk_d2d(pipeline.q, self.peer_ptrs[r] + self.offset_bytes,
+                                         self.b.buffer + self.offset_bytes, self.share_bytes))
+
+    def release(self, pipeline) -> None:
+        pipeline.wait_and_cleanup()
+        for p in self._opened:
+            capi.check(capi.lib().wk_ipc_close_handle(pipeline.q, p))
+        self._opened = []
+
+
 class RowShardedC:
     """The full-size result matrix of one rank plus the peers' copies, mapped through CUDA IPC."""
 
@@ -59,24 +130,7 @@ class RowShardedC:
         self.row0, self.rows = shard_rows(m, world, rank)
         self.c = Tensor.alloc(context, pipeline, (m, n), dtype)
         pipeline.wait_and_cleanup()
-        lib = capi.lib()
-        self._opened = []
-        self.peer_ptrs = (C.c_void_p * world)()
-        if world == 1:
-            self.peer_ptrs[0] = self.c.buffer
-            return
-        handle = (C.c_ubyte * 64)()
-        capi.check(lib.wk_ipc_get_handle(pipeline.q, self.c.ptr, handle))
-        handles = exchange(bytes(handle), world, all_gather_object)
-        for r, h in enumerate(handles):
-            if r == rank:
-                self.peer_ptrs[r] = self.c.buffer
-                continue
-            buf = (C.c_ubyte * 64).from_buffer_copy(h)
-            p = C.c_void_p()
-            capi.check(lib.wk_ipc_open_handle(pipeline.q, buf, C.byref(p)))
-            self.peer_ptrs[r] = p.value
-            self._opened.append(p)
+        self.peer_ptrs, self._opened = map_on_peers(pipeline, self.c, rank, world, all_gather_object)
 
     def block(self, pipeline) -> Tensor:
         """view of this rank's row block of C"""
