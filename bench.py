@@ -417,7 +417,8 @@ def run_ours(args):
         hostbar = lambda: torch.distributed.barrier(group=gloo)
         ctx4 = wk.Context.init([local_rank] * 4)
         p_mm, p_up, p_dn, p_push = (wk.Pipeline.init(q) for q in ctx4.command_queues)
-        rep = rowshard.ReplicatedOperand(ctx4, p_mm, b, rank, world)
+        b4 = wk.Tensor.wrap(ctx4, p_mm, (N, N), dt, b.buffer)  # the same HBM, as a tensor of the 4-queue context
+        rep = rowshard.ReplicatedOperand(ctx4, p_mm, b4, rank, world)
         ha, pa = pinned_array(wk, (rows, N), dt)
         hb, pb = pinned_array(wk, (rep.rows, N), dt)
         hc, pc = pinned_array(wk, (rows, N), dt)
@@ -453,7 +454,7 @@ def run_ours(args):
             hostbar()                  # ... and every peer's share is in mine
             for i in range(n_panels):
                 p_mm.wait_for(evs[i])
-                wk.blas.gemm(p_mm, None, a_pan[i], 0, b, 0, None, c_pan[i])
+                wk.blas.gemm(p_mm, None, a_pan[i], 0, b4, 0, None, c_pan[i])
                 p_dn.wait_for(p_mm.record_event())
                 wtb(p_dn, c_pan[i], hc[bounds[i]:bounds[i + 1]].reshape(-1))
             p_mm.wait_for(p_dn.record_event())  # the step ends when the last panel of C is on the host

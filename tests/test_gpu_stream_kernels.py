@@ -81,7 +81,7 @@ def test_transpose2d_exact(dtype, shape):
         t.release(pipe)
 
 
-@pytest.mark.parametrize("op", ["tanh", "sigmoid"])
+@pytest.mark.parametrize("op", ["tanh", "sigmoid", "cosh"])
 def test_f64_activation_accuracy_and_special_values(op):
     """the branch-free f64 tanh / sigmoid (csrc/common.cuh) against numpy's libm over the whole range: a few ulp
     relative (the reference tests to 1e-5 absolute, trig.zig:129-446), exact limits, NaN kept, tiny arguments not
@@ -92,7 +92,7 @@ def test_f64_activation_accuracy_and_special_values(op):
     x = np.concatenate([
         rng.uniform(-1.5, 1.5, 20000), rng.uniform(-25, 25, 20000), rng.uniform(-760, 760, 20000),
         rng.uniform(0, 1, 20000) * 2.0 ** -rng.integers(0, 60, 20000) * rng.choice([-1.0, 1.0], 20000),
-        [0.0, -0.0, 1e-300, -1e-300, 19.9, 20.0, 20.1, 40.0, -40.0, 700.0, -700.0, 709.0, -745.0, 1e308, -1e308,
+        [0.0, -0.0, 1e-300, -1e-300, 19.9, 20.0, 20.1, 40.0, -40.0, 700.0, -700.0, 709.0, 710.47, -710.47, 710.48, 711.0, -745.0, 1e308, -1e308,
          np.inf, -np.inf, np.nan],
     ])
     x = np.resize(x, (len(x) // 2 * 2,)).reshape(2, -1)
@@ -101,6 +101,10 @@ def test_f64_activation_accuracy_and_special_values(op):
     if op == "tanh":
         wk.math.tanh(pipe, t)
         want = np.tanh(x.astype(np.longdouble)).astype(np.float64)
+    elif op == "cosh":
+        wk.math.cosh(pipe, t)
+        with np.errstate(over="ignore"):
+            want = np.cosh(x.astype(np.longdouble)).astype(np.float64)
     else:
         wk.nn.Sigmoid.init().run(pipe, t)
         with np.errstate(over="ignore"):
@@ -109,6 +113,7 @@ def test_f64_activation_accuracy_and_special_values(op):
     t.release(pipe)
     finite = np.isfinite(want)
     assert np.array_equal(np.isnan(got), np.isnan(x))
+    assert np.array_equal(np.isinf(got), np.isinf(want)) and np.all(got[np.isinf(want)] == want[np.isinf(want)])
     big = finite & (np.abs(want) > 1e-290)
     rel = np.abs(got[big] - want[big]) / np.abs(want[big])
     assert rel.max() <= 4 * np.finfo(np.float64).eps, rel.max()
