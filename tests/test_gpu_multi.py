@@ -21,7 +21,7 @@ def _n_gpus():
     return n.value
 
 
-def _worker(rank, world, port, dtype_name, op_a, op_b, q):
+def _worker(rank, world, port, dtype_name, op_a, op_b, q, mnk=(640, 512, 200)):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -35,7 +35,7 @@ def _worker(rank, world, port, dtype_name, op_a, op_b, q):
         dtype = np.dtype(dtype_name)
         ctx = wk.Context.init([rank])
         pipe = wk.Pipeline.init(ctx.command_queues[0])
-        M, N, K = 640, 512, 200
+        M, N, K = mnk
         rng = np.random.default_rng(3)  # same data on every rank
         ad = rng.uniform(-1, 1, (K, M) if op_a else (M, K)).astype(dtype)
         bd = rng.uniform(-1, 1, (N, K) if op_b else (K, N)).astype(dtype)
@@ -68,7 +68,8 @@ def _worker(rank, world, port, dtype_name, op_a, op_b, q):
 
 @pytest.mark.parametrize("dtype_name", ["float32", "float64"])
 @pytest.mark.parametrize("op_a,op_b", [(0, 0), (1, 1)])
-def test_rowsharded_gemm_fused_allgather_2gpu(dtype_name, op_a, op_b):
+@pytest.mark.parametrize("mnk", [(640, 512, 200), (600, 500, 2048), (1100, 1284, 96)])  # ragged tiles, partial chunks, split-K
+def test_rowsharded_gemm_fused_allgather_2gpu(dtype_name, op_a, op_b, mnk):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -80,7 +81,7 @@ def test_rowsharded_gemm_fused_allgather_2gpu(dtype_name, op_a, op_b):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dtype_name, op_a, op_b, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dtype_name, op_a, op_b, q, mnk)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted(q.get(timeout=300) for _ in range(world))

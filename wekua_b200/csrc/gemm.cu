@@ -53,11 +53,16 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
             return WK_ERR_INVALID_VALUE;
         }
     }
-    if (peers && peers->n > 1) {
-        set_error("gemm: fused all-gather epilogue needs the tensor-core path (f32/f64, 16-byte aligned pitches)");
-        return WK_ERR_INVALID_VALUE;
+    int32_t rc = gemm_simt(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
+    if (rc != WK_OK || !peers || peers->n <= 1) return rc;
+    // operands the tensor-core kernels cannot address (e.g. a transposed A block starting at a row that is not a multiple of
+    // 16 bytes): the SIMT kernel has no fused epilogue, so the finished block follows to the peers as pitched copies
+    const size_t es = dtype_size(dtype);
+    for (int i = 0; i < peers->n; i++) {
+        if (i == peers->self) continue;
+        WK_CUDA(cudaMemcpy2DAsync(peers->ptrs[i], ldc * es, C, ldc * es, N * es, M, cudaMemcpyDeviceToDevice, q->stream));
     }
-    return gemm_simt(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
+    return WK_OK;
 }
 // Complex(T) GEMM (ids 10-19; the reference's complex branches: gemm_2x2.cl:121-236, gemm_nxn.cl:383-398) as ONE real
 // GEMM of shape M x 2N x 2K on the real back-ends -- derivation and operand layouts in complex.cu.

@@ -66,6 +66,7 @@ struct Params {
     float *ws;
     unsigned *tickets;
     int n_peers, self;
+    int peer_bulk;  // fused all-gather: peers receive whole 128-byte row segments as bulk async copies from the staging tile
     float *peers[16];
 };
 
@@ -337,8 +338,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                         const float4 out = make_float4(v[0], v[1], v[2], v[3]);
                         *reinterpret_cast<float4 *>(cp) = out;
-                        for (int pi = 0; pi < p.n_peers; pi++)
-                            if (pi != p.self) *reinterpret_cast<float4 *>(p.peers[pi] + row * p.ldc + col) = out;
+                        if (p.peer_bulk) {  // the finished values go back into the staging tile; the copy engine ships them
+                            *reinterpret_cast<float4 *>(epi + rl * EPI_PITCH + (lane & 7) * 4) = out;
+                        } else {
+                            for (int pi = 0; pi < p.n_peers; pi++)
+                                if (pi != p.self) *reinterpret_cast<float4 *>(p.peers[pi] + row * p.ldc + col) = out;
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
@@ -353,6 +358,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             }
                         }
                     }
+                }
+                if (p.peer_bulk) {
+                    // Register stores to a peer hold the warp for an NVLink round trip each (448 per warp and tile with 7
+                    // peers: the epilogue took about as long as the tile's MMAs).  Instead every lane hands ITS row of the
+                    // finished chunk -- one 128-byte segment -- to the bulk-copy engine once per peer and moves on; only the
+                    // shared-memory read has to be over before the staging tile is reused.
+                    fence_proxy_async();
+                    __syncwarp();
+                    const uint64_t row = row0 + lane, colc = col0 + (uint64_t)c * 32;
+                    if (row < p.M && colc < p.N) {
+                        const uint32_t bytes = (uint32_t)((p.N - colc < 32 ? p.N - colc : 32) * 4);
+                        const uint32_t src = smem_u32(epi + lane * EPI_PITCH);
+                        for (int pi = 0; pi < p.n_peers; pi++)
+                            if (pi != p.self)
+                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                                                 p.peers[pi] + row * p.ldc + colc),
+                                             "r"(src), "r"(bytes)
+                                             : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
                 __syncwarp();  // the tile is overwritten by the next chunk
             };
@@ -462,6 +488,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
+        // bulk copies to the peers: complete (written, not only read) before this CTA is allowed to finish
+        if (p.peer_bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -599,10 +627,13 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
                 (unsigned long long)units_avail, (unsigned long long)n_full, p.splits, p.kb_per_split);
     p.n_peers = 0;
     p.self = 0;
+    p.peer_bulk = 0;
     if (peers && peers->n > 1) {
         p.n_peers = peers->n;
         p.self = peers->self;
         for (int i = 0; i < peers->n; i++) p.peers[i] = (float *)peers->ptrs[i];
+        static const int bulk_env = env_int("WK_GEMM_PEER_BULK", 1);
+        p.peer_bulk = bulk_env && peers->n > 1 && N % 4 == 0;  // whole 16-byte pieces per row segment
     }
 
     const uint64_t num_tiles = n_full + n_split_tiles * p.splits;
