@@ -121,3 +121,25 @@ def test_f64_activation_accuracy_and_special_values(op):
     if op == "tanh":
         assert np.array_equal(np.signbit(got[~np.isnan(x)]), np.signbit(x[~np.isnan(x)]))
         assert got[x == np.inf][0] == 1.0 and got[x == -np.inf][0] == -1.0
+
+
+def test_f64_tan_accuracy():
+    """branch-free f64 tan (csrc/common.cuh: Cody-Waite by pi/2, sin/cos kernels, one quotient) against long-double libm:
+    small, moderate and large arguments, the libdevice hand-over at 1e5, signed zero"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(19)
+    x = np.concatenate([rng.uniform(-1.5, 1.5, 20000), rng.uniform(-100, 100, 20000), rng.uniform(-1e5, 1e5, 20000),
+                        rng.uniform(-1e7, 1e7, 20000), rng.uniform(0, 1, 5000) * 2.0 ** -rng.integers(0, 200, 5000),
+                        [0.0, -0.0, 99999.9, 100000.0, 100000.1, np.pi / 4, -np.pi / 4, 1e-300, 1e300]])
+    x = np.resize(x, (len(x) // 2 * 2,)).reshape(2, -1)
+    t = wk.Tensor.alloc(ctx, pipe, x.shape, np.float64)
+    wk.tensor.memory.read_from_buffer(pipe, t, x)
+    wk.math.tan(pipe, t)
+    got = gh.to_np(t)
+    t.release(pipe)
+    want = np.tan(x.astype(np.longdouble)).astype(np.float64)
+    nz = want != 0
+    rel = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
+    assert rel.max() <= 6 * np.finfo(np.float64).eps, rel.max()
+    assert np.array_equal(got[~nz], x[~nz]) and np.array_equal(np.signbit(got[~nz]), np.signbit(x[~nz]))

@@ -236,6 +236,8 @@ template <typename T> struct FillF {  // fill.cl:11-16
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const { v[0] = value; }
 };
 
+__device__ __forceinline__ float wk_tan(float x) { return tanf(x); }
+__device__ __forceinline__ double wk_tan(double x) { return wk_tan_f64(x); }
 __device__ __forceinline__ float wk_cosh(float x) { return coshf(x); }
 __device__ __forceinline__ double wk_cosh(double x) { return wk_cosh_f64(x); }
 __device__ __forceinline__ float wk_tanh(float x) { return tanhf(x); }
@@ -249,7 +251,7 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
         const T x = v[0];
         if (OP == WK_OP_SIN) v[0] = sin(x);
         else if (OP == WK_OP_COS) v[0] = cos(x);
-        else if (OP == WK_OP_TAN) v[0] = tan(x);
+        else if (OP == WK_OP_TAN) v[0] = wk_tan(x);
         else if (OP == WK_OP_SINH) v[0] = sinh(x);
         else if (OP == WK_OP_COSH) v[0] = wk_cosh(x);
         else if (OP == WK_OP_TANH) v[0] = wk_tanh(x);
@@ -257,10 +259,8 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
     }
 };
 
-// libdevice's f64 tan is issue-bound and register-hungry: the deeper unroll only costs occupancy there (measured
-// 0.73 -> 0.65 of the copy bandwidth), so it keeps 4 vectors in flight.  (f64 tanh / cosh / sigmoid were in the same
-// position until they got the branch-free constant-bank implementations of common.cuh: 0.65 / 0.86 / 0.84 -> 0.92+.)
-template <> struct KeepShallow<UnaryF<double, WK_OP_TAN>> : std::true_type {};
+// (libdevice's f64 tan / tanh / cosh and the IEEE division of sigmoid were issue-bound here -- 0.70 / 0.65 / 0.86 / 0.84 of the
+// copy bandwidth -- until they got the branch-free constant-bank implementations of common.cuh; no map needs KeepShallow now.)
 
 template <typename BT, int OP> struct UnaryF<Cx<BT>, OP> {  // trig.cl:5-66, complex branches
     static constexpr unsigned kRead = 1, kWrite = 1;
