@@ -236,6 +236,10 @@ template <typename T> struct FillF {  // fill.cl:11-16
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const { v[0] = value; }
 };
 
+__device__ __forceinline__ float wk_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double wk_sin(double x) { return wk_sin_f64(x); }
+__device__ __forceinline__ float wk_cos(float x) { return cosf(x); }
+__device__ __forceinline__ double wk_cos(double x) { return wk_cos_f64(x); }
 __device__ __forceinline__ float wk_tan(float x) { return tanf(x); }
 __device__ __forceinline__ double wk_tan(double x) { return wk_tan_f64(x); }
 __device__ __forceinline__ float wk_cosh(float x) { return coshf(x); }
@@ -249,8 +253,8 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
     static constexpr unsigned kRead = 1, kWrite = 1;
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const {
         const T x = v[0];
-        if (OP == WK_OP_SIN) v[0] = sin(x);
-        else if (OP == WK_OP_COS) v[0] = cos(x);
+        if (OP == WK_OP_SIN) v[0] = wk_sin(x);
+        else if (OP == WK_OP_COS) v[0] = wk_cos(x);
         else if (OP == WK_OP_TAN) v[0] = wk_tan(x);
         else if (OP == WK_OP_SINH) v[0] = sinh(x);
         else if (OP == WK_OP_COSH) v[0] = wk_cosh(x);
