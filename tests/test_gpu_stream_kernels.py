@@ -143,3 +143,33 @@ def test_f64_tan_accuracy():
     rel = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
     assert rel.max() <= 6 * np.finfo(np.float64).eps, rel.max()
     assert np.array_equal(got[~nz], x[~nz]) and np.array_equal(np.signbit(got[~nz]), np.signbit(x[~nz]))
+
+
+@pytest.mark.parametrize("op", ["sin", "cos"])
+def test_f64_sin_cos_accuracy(op):
+    """f64 sin / cos on the same reduction as tan (quadrant picks the fdlibm kernel and the sign): relative accuracy for
+    moderate arguments, absolute accuracy up to the libdevice hand-over at 1e5 and beyond it, signed zero, non-finite"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(23)
+    parts = [rng.uniform(-1.5, 1.5, 20000), rng.uniform(-100, 100, 20000), rng.uniform(-1e5, 1e5, 20000),
+             rng.uniform(-1e7, 1e7, 20000), rng.uniform(0, 1, 5000) * 2.0 ** -rng.integers(0, 200, 5000),
+             np.array([0.0, -0.0, 99999.9, 100000.0, 100000.1, np.pi / 2, -np.pi / 2, np.pi, 1e-300, 1e300, np.inf, -np.inf, np.nan])]
+    x = np.concatenate(parts)
+    x = np.resize(x, (len(x) // 2 * 2,)).reshape(2, -1)
+    t = wk.Tensor.alloc(ctx, pipe, x.shape, np.float64)
+    wk.tensor.memory.read_from_buffer(pipe, t, x)
+    getattr(wk.math, op)(pipe, t)
+    got = gh.to_np(t)
+    t.release(pipe)
+    fin = np.isfinite(x)
+    assert np.all(np.isnan(got[~fin]))
+    with np.errstate(invalid="ignore"):
+        want = getattr(np, op)(x.astype(np.longdouble)).astype(np.float64)
+    eps = np.finfo(np.float64).eps
+    assert np.abs(got[fin] - want[fin]).max() <= 1.5 * eps
+    mod = fin & (np.abs(x) <= 100) & (want != 0)
+    assert (np.abs(got[mod] - want[mod]) / np.abs(want[mod])).max() <= 4 * eps
+    if op == "sin":
+        z = x == 0
+        assert np.array_equal(np.signbit(got[z]), np.signbit(x[z])) and np.all(got[z] == 0)
