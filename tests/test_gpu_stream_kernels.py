@@ -173,3 +173,37 @@ def test_f64_sin_cos_accuracy(op):
     if op == "sin":
         z = x == 0
         assert np.array_equal(np.signbit(got[z]), np.signbit(x[z])) and np.all(got[z] == 0)
+
+
+@pytest.mark.parametrize("op", ["sin", "cos", "tan"])
+def test_f32_trig_accuracy(op):
+    """f32 sin / cos / tan (branch-free fast path, libdevice slow path out of line at |x| >= 105615): against float64 libm"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(29)
+    parts = [rng.uniform(-1.5, 1.5, 20000), rng.uniform(-100, 100, 20000), rng.uniform(-1e5, 1e5, 20000),
+             rng.uniform(-1e7, 1e7, 20000), rng.uniform(0, 1, 5000) * 2.0 ** -rng.integers(0, 100, 5000),
+             np.array([0.0, -0.0, 105614.0, 105615.0, 105616.0, np.pi / 4, -np.pi / 4, np.pi, 1e-30, 1e30, np.inf, -np.inf, np.nan])]
+    x = np.concatenate(parts).astype(np.float32)
+    x = np.resize(x, (len(x) // 2 * 2,)).reshape(2, -1)
+    t = wk.Tensor.alloc(ctx, pipe, x.shape, np.float32)
+    wk.tensor.memory.read_from_buffer(pipe, t, x)
+    getattr(wk.math, op)(pipe, t)
+    got = gh.to_np(t).astype(np.float64)
+    t.release(pipe)
+    fin = np.isfinite(x)
+    assert np.all(np.isnan(got[~fin]))
+    with np.errstate(invalid="ignore"):
+        want = getattr(np, op)(x.astype(np.float64))
+    eps = float(np.finfo(np.float32).eps)
+    nz = fin & (want != 0)
+    rel = np.abs(got[nz] - want[nz]) / np.abs(want[nz])
+    if op == "tan":
+        assert rel.max() <= 6 * eps, rel.max()
+    else:
+        assert np.abs(got[fin] - want[fin]).max() <= 1.5 * eps
+        mod = nz & (np.abs(x) <= 100)
+        assert (np.abs(got[mod] - want[mod]) / np.abs(want[mod])).max() <= 4 * eps
+    if op != "cos":
+        z = x == 0
+        assert np.array_equal(np.signbit(got[z]), np.signbit(x[z])) and np.all(got[z] == 0)

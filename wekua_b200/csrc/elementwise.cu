@@ -236,11 +236,11 @@ template <typename T> struct FillF {  // fill.cl:11-16
     __device__ __forceinline__ void operator()(T (&v)[1], uint64_t) const { v[0] = value; }
 };
 
-__device__ __forceinline__ float wk_sin(float x) { return sinf(x); }
+__device__ __forceinline__ float wk_sin(float x) { return wk_sin_f32(x); }
 __device__ __forceinline__ double wk_sin(double x) { return wk_sin_f64(x); }
-__device__ __forceinline__ float wk_cos(float x) { return cosf(x); }
+__device__ __forceinline__ float wk_cos(float x) { return wk_cos_f32(x); }
 __device__ __forceinline__ double wk_cos(double x) { return wk_cos_f64(x); }
-__device__ __forceinline__ float wk_tan(float x) { return tanf(x); }
+__device__ __forceinline__ float wk_tan(float x) { return wk_tan_f32(x); }
 __device__ __forceinline__ double wk_tan(double x) { return wk_tan_f64(x); }
 __device__ __forceinline__ float wk_cosh(float x) { return coshf(x); }
 __device__ __forceinline__ double wk_cosh(double x) { return wk_cosh_f64(x); }
