@@ -154,6 +154,39 @@ def pinned_array(wk, shape, dtype):
     return arr, p
 
 
+def numa_local_host_memory(torch, local_rank):
+    """Place this process's future pinned host buffers (and, where the cpuset allows, its threads) on the NUMA node the
+    GPU hangs off: with one process per GPU the default policy puts every rank's staging memory wherever the process
+    happens to run, and half of the GPUs then DMA across the socket interconnect.  Best effort: returns what was done."""
+    if os.environ.get("WK_NUMA", "1") == "0":
+        return {"numa": "off"}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa": "single-node", "bdf": bdf}
+        done = {"numa": node, "bdf": bdf}
+        libc = C.CDLL(None, use_errno=True)
+        mask = C.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, C.byref(mask), 65)  # set_mempolicy(MPOL_PREFERRED, {node})
+        done["mempolicy"] = "preferred" if rc == 0 else f"errno {C.get_errno()}"
+        try:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                done["cpus"] = len(allowed)
+        except OSError:
+            pass
+        return done
+    except Exception as e:  # no sysfs entry, no such attribute, syscall refused: keep the default placement
+        return {"numa": f"unavailable ({type(e).__name__})"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_gemm(n, dtype, steps, warmup, vw_f32=None):
     """the restated reference CPU path: PackedTensors + gemm_pack.cl x2 + gemm_nxn_pack.cl per call
@@ -302,8 +335,12 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = None
     if world > 1:
         torch.cuda.set_device(local_rank)
+        numa = numa_local_host_memory(torch, local_rank)
+        if os.environ.get("WK_DEBUG"):
+            print(f"[bench] rank {rank}: host memory placement {numa}", file=sys.stderr, flush=True)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.gpus != world:
         if rank == 0:
@@ -479,7 +516,7 @@ def run_ours(args):
             assert abs(got_ - want) <= 1e-3 * max(1.0, abs(want)), (rank, i_, j_, got_, want)
         e2e = {"value": flops * e_steps / (ems * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(2 * N * N * 4), "d2h_bytes_per_step": int(N * N * 4),
-               "nvlink_bytes_per_step": int((g - 1) * N * N * 4),
+               "nvlink_bytes_per_step": int((g - 1) * N * N * 4), "host_memory": numa,
                "steps": e_steps, "ms_per_step": ems / e_steps,
                "how": (f"per rank, 4 queues on its device: upload 1/{g} of B's rows from pinned host memory, push that share to "
                        f"the {g - 1} peers over NVLink (IPC-mapped copies), upload {n_panels} row panels of its A block, host "

@@ -93,3 +93,60 @@ def test_rowsharded_gemm_fused_allgather_2gpu(dtype_name, op_a, op_b):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in results), results
+
+
+def _worker_replicated(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import wekua_b200 as wk
+    from wekua_b200 import rowshard as rs
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ctx = wk.Context.init([rank, rank])
+        p_up, p_push = (wk.Pipeline.init(cq) for cq in ctx.command_queues)
+        ok = True
+        for shape, dtype in (((301, 130), np.float32), ((64, 7), np.float64)):  # ragged shares, a padded pitch (7 -> 8)
+            full = np.random.default_rng(5).uniform(-1, 1, shape).astype(dtype)  # the same matrix in every process
+            b = wk.Tensor.alloc(ctx, p_up, shape, dtype)
+            rep = rs.ReplicatedOperand(ctx, p_up, b, rank, world)
+            dist.barrier()
+            rep.upload_share(p_up, np.ascontiguousarray(full[rep.row0:rep.row0 + rep.rows]))
+            p_push.wait_for(p_up.record_event())
+            rep.push_share(p_push)
+            p_push.wait_and_cleanup()
+            dist.barrier()  # every share has landed everywhere
+            got = wk.tensor.memory.to_numpy(p_up, b)
+            ok &= bool(np.array_equal(got, full))
+            dist.barrier()
+            rep.release(p_up)
+            b.release(p_up)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicated_operand_shared_upload_2gpu():
+    """B of the row-sharded product from HOST memory: each rank uploads its share of the rows and pushes it to the peer over
+    NVLink; afterwards every rank holds the whole matrix, bit for bit"""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_replicated, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert results == [(0, True), (1, True)], results
