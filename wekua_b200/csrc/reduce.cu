@@ -4,6 +4,8 @@
 // 128-bit streaming read with warp-shuffle + shared-memory block reduction into per-block partials, stage 2 a
 // single block folding the partials; the scalar then travels through pinned memory (the reference blocks on a
 // mapped read at the same point, basic.zig:154-171).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace wk {
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restr
                                                                 uint64_t run_len, uint64_t n_runs, uint64_t rows,
                                                                 uint64_t xrp, uint64_t xsp, uint64_t yrp, uint64_t ysp,
                                                                 typename Acc<T>::type *partial, unsigned *ticket,
-                                                                T *__restrict__ out) {
+                                                                T *__restrict__ out, unsigned *posted, unsigned seq) {
     using A = typename Acc<T>::type;
     constexpr int VEC = 16 / (int)sizeof(T);
     union Pack { uint4 u; T e[VEC]; };
@@ -118,6 +120,10 @@ __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restr
     if (threadIdx.x == 0) {
         *out = from_acc<T>(f);
         *ticket = 0;
+        if (posted) {  // blocking form: `out` is pinned host memory; tell the polling host thread the scalar has landed
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(posted) = seq;
+        }
     }
 }
 
@@ -149,16 +155,32 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     // blocking form: the fold kernel stores the scalar straight into the queue's pinned host word (device-addressable
     // under UVA), so the only thing after it is the stream synchronisation the reference's mapped read implies
     T *result = device_out ? reinterpret_cast<T *>(device_out) : reinterpret_cast<T *>(q->pinned);
+    unsigned *posted = device_out ? nullptr : reinterpret_cast<unsigned *>((char *)q->pinned + 128);
+    const unsigned seq = device_out ? 0 : ++q->reduce_seq;
     dim3 grid((unsigned)gx, (unsigned)gy);
     if (vec)
         reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial,
-                                                                           q->reduce_ticket, result);
+                                                                           q->reduce_ticket, result, posted, seq);
     else
         reduce_runs_kernel<T, NIN, false><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial,
-                                                                            q->reduce_ticket, result);
+                                                                            q->reduce_ticket, result, posted, seq);
     WK_CHECK_LAUNCH();
     if (device_out) return WK_OK;  // async form: the scalar stays on the device, stream-ordered
-    WK_CUDA(cudaStreamSynchronize(q->stream));
+    // The reference blocks on a mapped read here (basic.zig:154-171).  Waking up from cudaStreamSynchronize costs 5-8 us
+    // after the kernel has finished; the last block posts a sequence number next to the scalar instead and this thread
+    // polls the pinned word (checking the stream every ~50 us so that a failed launch surfaces as an error, not a hang).
+    volatile unsigned *flag = reinterpret_cast<volatile unsigned *>((char *)q->pinned + 128);
+    for (unsigned spins = 0; *flag != seq; spins++) {
+        if ((spins & 0x3ff) == 0x3ff) {
+            const cudaError_t st = cudaStreamQuery(q->stream);
+            if (st == cudaSuccess) break;  // everything enqueued has run: the scalar is there
+            if (st != cudaErrorNotReady) return cuda_fail(st, "cudaStreamQuery (blocking reduction)", __FILE__, __LINE__);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     memcpy(host_out, q->pinned, sizeof(T));
     return WK_OK;
 }

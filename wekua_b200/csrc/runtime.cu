@@ -92,6 +92,7 @@ static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t ad
         q->owns_stream = true;
     }
     WK_CUDA(cudaMallocHost(&q->pinned, 256));
+    memset(q->pinned, 0, 256);
     WK_CUDA(cudaMalloc((void **)&q->reduce_ticket, 64));
     WK_CUDA(cudaMemset(q->reduce_ticket, 0, 64));
     return WK_OK;
