@@ -455,11 +455,21 @@ def run_ours(args):
         ctx4 = wk.Context.init([local_rank] * 4)
         p_mm, p_up, p_dn, p_push = (wk.Pipeline.init(q) for q in ctx4.command_queues)
         b4 = wk.Tensor.wrap(ctx4, p_mm, (N, N), dt, b.buffer)  # the same HBM, as a tensor of the 4-queue context
-        rep = rowshard.ReplicatedOperand(ctx4, p_mm, b4, rank, world)
+        # B lives in HBM as NJ dense column panels: panel j is uploaded (1/g per rank), pushed to the peers, fenced and
+        # multiplied while the later panels are still crossing PCIe -- the step is upload-bound, so what matters is that
+        # little work is left after the LAST piece has arrived.  A (the rank's row block) follows B's first panel.
+        NJ = int(os.environ.get("WK_E2E_NJ_MULTI", 8))
+        if N % (2 * NJ) or b4.row_pitch != N:
+            NJ = 1
+        nc = N // NJ
+        rep = rowshard.ReplicatedOperand(ctx4, p_mm, b4, rank, world, col_panels=NJ)
         ha, pa = pinned_array(wk, (rows, N), dt)
-        hb, pb = pinned_array(wk, (rep.rows, N), dt)
-        hc, pc = pinned_array(wk, (rows, N), dt)
-        pins = [pa, pb, pc]
+        pins = [pa]
+        hbs, hcs = [], []
+        for _ in range(NJ):
+            hb_, pb_ = pinned_array(wk, (rep.rows, nc), dt)
+            hc_, pc_ = pinned_array(wk, (rows, nc), dt)
+            hbs.append(hb_); hcs.append(hc_); pins += [pb_, pc_]
         P = 512
         blk = np.random.default_rng(7).uniform(-1, 1, (P, N)).astype(dt)  # A rows repeat blk, B rows repeat blk reversed
         for r0 in range(0, rows, P):
@@ -467,33 +477,40 @@ def run_ours(args):
         brev = blk[::-1]
         for r0 in range(0, rep.rows, P):  # global row r of B is brev[r % P]
             idx = (rep.row0 + r0 + np.arange(min(P, rep.rows - r0))) % P
-            hb[r0:r0 + len(idx)] = brev[idx]
-        n_panels = max(1, min(int(os.environ.get("WK_E2E_PANELS", 8)), rows // 1024))
+            for jj in range(NJ):
+                hbs[jj][r0:r0 + len(idx)] = brev[idx, jj * nc:(jj + 1) * nc]
+        n_panels = max(1, min(int(os.environ.get("WK_E2E_PANELS", 8)), rows // 4096))
         bounds = [rows * i // n_panels for i in range(n_panels + 1)]
         es = np.dtype(dt).itemsize
         a_pan = [wk.Tensor.wrap(ctx4, p_mm, (bounds[i + 1] - bounds[i], N), dt, a.buffer + bounds[i] * a.row_pitch * es)
                  for i in range(n_panels)]
-        c_pan = [wk.Tensor.wrap(ctx4, p_mm, (bounds[i + 1] - bounds[i], N), dt, c_blk.buffer + bounds[i] * c_blk.row_pitch * es)
-                 for i in range(n_panels)]
+        c_pan = [[wk.Tensor.wrap(ctx4, p_mm, (bounds[i + 1] - bounds[i], nc), dt,
+                                 c_blk.buffer + (bounds[i] * c_blk.row_pitch + jj * nc) * es, row_pitch=c_blk.row_pitch)
+                  for i in range(n_panels)] for jj in range(NJ)]
         rfb, wtb = wk.tensor.memory.read_from_buffer, wk.tensor.memory.write_to_buffer
 
         def e2e_step():
             p_mm.wait_and_cleanup()  # my products of the previous step have read B ...
             hostbar()                # ... and so have everybody else's: B may be overwritten
-            rep.upload_share(p_up, hb)
-            p_push.wait_for(p_up.record_event())
-            rep.push_share(p_push)
-            evs = []
-            for i in range(n_panels):
-                rfb(p_up, a_pan[i], ha[bounds[i]:bounds[i + 1]])
-                evs.append(p_up.record_event())
-            p_push.wait_and_cleanup()  # my share is in every peer's B ...
-            hostbar()                  # ... and every peer's share is in mine
-            for i in range(n_panels):
-                p_mm.wait_for(evs[i])
-                wk.blas.gemm(p_mm, None, a_pan[i], 0, b4, 0, None, c_pan[i])
-                p_dn.wait_for(p_mm.record_event())
-                wtb(p_dn, c_pan[i], hc[bounds[i]:bounds[i + 1]].reshape(-1))
+            pushed, a_ev = [], []
+            for jj in range(NJ):
+                rep.upload_share(p_up, hbs[jj], jj)
+                p_push.wait_for(p_up.record_event())
+                rep.push_share(p_push, jj)
+                pushed.append(p_push.record_event())
+                if jj == 0:
+                    for i in range(n_panels):
+                        rfb(p_up, a_pan[i], ha[bounds[i]:bounds[i + 1]])
+                        a_ev.append(p_up.record_event())
+            for jj in range(NJ):
+                wk.capi.check(wk.capi.lib().wk_event_wait(pushed[jj]))  # my share of panel jj is in every peer's B ...
+                hostbar()                                                # ... and every peer's share is in mine
+                for i in range(n_panels):
+                    if jj == 0:
+                        p_mm.wait_for(a_ev[i])
+                    wk.blas.gemm(p_mm, None, a_pan[i], 0, rep.panels[jj], 0, None, c_pan[jj][i])
+                    p_dn.wait_for(p_mm.record_event())
+                    wtb(p_dn, c_pan[jj][i], hcs[jj][bounds[i]:bounds[i + 1]].reshape(-1))
             p_mm.wait_for(p_dn.record_event())  # the step ends when the last panel of C is on the host
             p_up.wait_for(p_mm.record_event())
 
@@ -512,15 +529,15 @@ def run_ours(args):
         for (i_, j_) in ((0, 0), (rows - 1, N - 1), (rows // 2, 17)):  # the product did reach the host
             bcol = np.tile(brev[:, j_].astype(np.float64), (N + P - 1) // P)[:N]
             want = float(ha[i_].astype(np.float64) @ bcol)
-            got_ = float(hc[i_, j_])
+            got_ = float(hcs[j_ // nc][i_, j_ % nc])
             assert abs(got_ - want) <= 1e-3 * max(1.0, abs(want)), (rank, i_, j_, got_, want)
         e2e = {"value": flops * e_steps / (ems * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(2 * N * N * 4), "d2h_bytes_per_step": int(N * N * 4),
                "nvlink_bytes_per_step": int((g - 1) * N * N * 4), "host_memory": numa,
                "steps": e_steps, "ms_per_step": ems / e_steps,
-               "how": (f"per rank, 4 queues on its device: upload 1/{g} of B's rows from pinned host memory, push that share to "
-                       f"the {g - 1} peers over NVLink (IPC-mapped copies), upload {n_panels} row panels of its A block, host "
-                       "barrier, multiply panel by panel, download each finished panel of C")}
+               "how": (f"per rank, 4 queues on its device: B as {NJ} column panels, each uploaded 1/{g} per rank from pinned host "
+                       f"memory and pushed to the {g - 1} peers over NVLink (IPC-mapped copies); the rank's A block ({n_panels} row "
+                       "panel(s)) follows B's first panel; per column panel a host barrier, then multiply and download C")}
         barrier()
         rep.release(p_mm)
         for p in pins:

@@ -124,6 +124,22 @@ def _worker_replicated(rank, world, port, q):
             dist.barrier()
             rep.release(p_up)
             b.release(p_up)
+        # column panels: B kept as dense [rows, cols / 2] panels one after the other; panel by panel upload + push
+        full = np.random.default_rng(6).uniform(-1, 1, (66, 12)).astype(np.float32)
+        b = wk.Tensor.alloc(ctx, p_up, full.shape, np.float32)
+        rep = rs.ReplicatedOperand(ctx, p_up, b, rank, world, col_panels=2)
+        dist.barrier()
+        for j in range(2):
+            rep.upload_share(p_up, np.ascontiguousarray(full[rep.row0:rep.row0 + rep.rows, j * 6:(j + 1) * 6]), j)
+            p_push.wait_for(p_up.record_event())
+            rep.push_share(p_push, j)
+        p_push.wait_and_cleanup()
+        dist.barrier()
+        for j in range(2):
+            ok &= bool(np.array_equal(wk.tensor.memory.to_numpy(p_up, rep.panels[j]), full[:, j * 6:(j + 1) * 6]))
+        dist.barrier()
+        rep.release(p_up)
+        b.release(p_up)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -87,32 +87,46 @@ class ReplicatedOperand:
     the peers' buffers over NVLink (copy engines, CUDA-IPC mapped pointers) -- world x less host traffic than every
     rank uploading the whole matrix.  The caller orders the steps: `upload_share` on an upload queue, `push_share`
     on a queue that waits for it, then a host-side barrier after the push queue has drained (every share has landed
-    everywhere) before the product reads B, and another one before the next upload overwrites it."""
+    everywhere) before the product reads B, and another one before the next upload overwrites it.
 
-    def __init__(self, context, pipeline, b: Tensor, rank: int, world: int, all_gather_object=None):
-        self.context, self.b, self.rank, self.world = context, b, rank, world
-        self.row0, self.rows, self.offset_bytes, self.share_bytes = share_span(b.shape[0], b.row_pitch, b.dtype.itemsize,
-                                                                               world, rank)
+    col_panels > 1 keeps B in HBM as that many dense column panels [rows, cols / col_panels], one after the other
+    (`panels[j]` are the tensors to multiply by), so that panel j can be uploaded, pushed, fenced and multiplied while
+    the later panels are still on their way; the share of a panel is again the rank's block of its rows."""
+
+    def __init__(self, context, pipeline, b: Tensor, rank: int, world: int, all_gather_object=None, col_panels: int = 1):
+        self.context, self.b, self.rank, self.world, self.col_panels = context, b, rank, world, col_panels
+        rows_total, cols = b.shape
+        es = b.dtype.itemsize
+        if col_panels < 1 or cols % col_panels or (col_panels > 1 and (b.row_pitch != cols or (cols // col_panels) % 2)):
+            raise capi.InvalidValue("InvalidValue: column panels need a dense B and an even number of columns per panel")
+        nc = cols // col_panels
+        pitch = b.row_pitch if col_panels == 1 else nc
+        self.row0, self.rows, off, self.share_bytes = share_span(rows_total, pitch, es, world, rank)
         pipeline.wait_and_cleanup()
         self.peer_ptrs, self._opened = map_on_peers(pipeline, b, rank, world, all_gather_object)
-        self.share = Tensor.wrap(context, pipeline, (self.rows, b.shape[1]), b.dtype, b.buffer + self.offset_bytes,
-                                 row_pitch=b.row_pitch)
+        panel_bytes = rows_total * pitch * es
+        self.offsets = [j * panel_bytes + off for j in range(col_panels)]
+        self.panels = [b] if col_panels == 1 else [
+            Tensor.wrap(context, pipeline, (rows_total, nc), b.dtype, b.buffer + j * panel_bytes) for j in range(col_panels)]
+        self.shares = [Tensor.wrap(context, pipeline, (self.rows, nc), b.dtype, b.buffer + self.offsets[j], row_pitch=pitch)
+                       for j in range(col_panels)]
+        self.offset_bytes, self.share = self.offsets[0], self.shares[0]
 
-    def upload_share(self, pipeline, host_rows: np.ndarray) -> None:
-        """host_rows: this rank's rows [row0, row0 + rows) of B, dense"""
+    def upload_share(self, pipeline, host_rows: np.ndarray, panel: int = 0) -> None:
+        """host_rows: this rank's rows [row0, row0 + rows) of column panel `panel` of B, dense"""
         from .tensor import memory
 
-        if host_rows.shape != (self.rows, self.b.shape[1]):
+        if host_rows.shape != tuple(self.shares[panel].shape):
             raise capi.InvalidValue("InvalidValue: host share does not match the rank's rows of B")
-        memory.read_from_buffer(pipeline, self.share, host_rows)
+        memory.read_from_buffer(pipeline, self.shares[panel], host_rows)
 
-    def push_share(self, pipeline) -> None:
-        """copy this rank's share into every peer's B at the same offset (NVLink, one copy per peer, rotated so that
-        the ranks do not all target the same peer first)"""
+    def push_share(self, pipeline, panel: int = 0) -> None:
+        """copy this rank's share of a panel into every peer's B at the same offset (NVLink, one copy per peer, rotated
+        so that the ranks do not all target the same peer first)"""
+        off = self.offsets[panel]
         for i in range(1, self.world):
             r = (self.rank + i) % self.world
-            capi.check(capi.lib().wk_d2d(pipeline.q, self.peer_ptrs[r] + self.offset_bytes,
-                                         self.b.buffer + self.offset_bytes, self.share_bytes))
+            capi.check(capi.lib().wk_d2d(pipeline.q, self.peer_ptrs[r] + off, self.b.buffer + off, self.share_bytes))
 
     def release(self, pipeline) -> None:
         pipeline.wait_and_cleanup()
