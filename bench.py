@@ -634,6 +634,20 @@ def run_ours(args):
         also.append(bench_gemm_single(wk, ctx, pipe, np.float64, 16384 if not args.small else 4096, max(3, s2 // 2), 3, peaks))
         also.append(bench_axpy(wk, ctx, pipe, np.float32, 1 << 28, 50, 5, peaks))
         also.append(bench_axpy(wk, ctx, pipe, np.float64, 1 << 28, 50, 5, peaks))
+    layer_step = None
+    if world == 1 and not args.quick:
+        # the other HBM-bound kernels of a layer step, same method as tools/stream_sweep.py:
+        # 2^27 elements per operand, CUDA events, algorithmic bytes / time against the measured copy bandwidth
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("wk_stream_sweep", os.path.join(ROOT, "tools", "stream_sweep.py"))
+        sw = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(sw)
+        rows_, _ = sw.sweep(27, only=("scal,hadamard (math.dot),sum,dot_reduce,sigmoid,tanh,sigmoid_dev,tanh_dev,"
+                                      "act_backward(sigmoid),bias_add,bias_step,mse (+dev),gdm,adagrad,rmsprop,adam"),
+                            ctx=ctx, pipe=pipe, reps=10, warm=3, verbose=False)
+        layer_step = [{"op": r_["op"], "dtype": r_["dtype"], "bytes_per_elem": r_["bytes_per_elem"], "gbs": round(r_["gbs"], 1),
+                       "frac": round(r_["gbs"] / peaks["hbm_gbs"], 3)} for r_ in rows_]
     if world > 1 and not args.quick:  # "AXPY HBM GB/s at 1/2/4/8 B200": every rank streams its own vectors
         for dt_ in (np.float32, np.float64):
             r_ = bench_axpy(wk, ctx, pipe, dt_, 1 << 28, 50, 5, peaks, barrier, max_over_ranks, world)
@@ -658,6 +672,9 @@ def run_ours(args):
                                       traffic=NCU_TRAFFIC_BYTES["gemm_f32_n32768_1gpu"] if (g == 1 and N == 32768) else None),
             "cpu_baseline": cpu, "also": also,
         }
+        if layer_step is not None:
+            line["layer_step_streaming"] = {"n": 1 << 27, "peak_gbs": peaks["hbm_gbs"], "peak_basis": f"{peaks['_source']} copy bandwidth",
+                                            "kernels": layer_step}
         if world > 1:
             line["gather_variants_tflops"] = variants
             line["gather_check"] = gather_check
