@@ -1,0 +1,30 @@
+"""-m "not gpu": the driver-facing scripts at least parse and import here (no GPU): bench.py's CLI, the streaming sweep
+module bench.py imports for `layer_step_streaming`, and the reference arm's JSON contract on a tiny sample."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_help_and_sweep_import():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "--impl" in r.stdout and "--gpus" in r.stdout
+    spec = importlib.util.spec_from_file_location("wk_stream_sweep_t", os.path.join(ROOT, "tools", "stream_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert callable(mod.sweep) and callable(mod.main)
+
+
+def test_reference_arm_contract_line():
+    """bench.py --impl reference on a small sub-problem: one JSON line with the keys the driver reads"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-n", "256"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "gemm_f32_tflops" and line["unit"] == "TFLOP/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
