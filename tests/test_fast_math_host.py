@@ -1,5 +1,5 @@
 """-m "not gpu": the branch-free transcendental replacements of wekua_b200/csrc/common.cuh (f64 tanh / sigmoid / cosh / tan /
-sin / cos, f32 sin / cos / tan), checked WITHOUT a GPU: the device functions are plain fma / add / mul sequences, so their
+sin / cos, f32 sin / cos / tan / cosh), checked WITHOUT a GPU: the device functions are plain fma / add / mul sequences, so their
 text is compiled for the host with a small shim (CUDA intrinsics -> libm, MUFU.RCP64H -> a 18-bit reciprocal, the libdevice
 slow paths -> libm) and compared with long-double libm over the ranges the GPU tests use.  This pins the ALGORITHM (constants,
 polynomial coefficients, operation order); tests/test_gpu_stream_kernels.py pins the device result."""
@@ -27,6 +27,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline int __double2loint(double t) { int64_t i; memcpy(&i, &t, 8); return (int)(int32_t)(i & 0xffffffff); }
 static inline int __double2hiint(double t) { int64_t i; memcpy(&i, &t, 8); return (int)(int32_t)(i >> 32); }
 static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &u, 8); return d; }
@@ -36,7 +37,7 @@ using std::fma; using std::fabs; using std::copysign;
 '''
 
 MAIN = r'''
-static double worst[9];
+static double worst[10];
 static void upd(int k, long double got, long double want) {
     if (want == 0 || !std::isfinite((double)want)) return;
     const double e = (double)fabsl((got - want) / want);
@@ -59,13 +60,16 @@ int main() {
         const float f = (float)y;
         upd(6, wk_tan_f32(f), tan((double)f));
         if (std::fabs(y) <= 100) { upd(7, wk_sin_f32(f), sin((double)f)); upd(8, wk_cos_f32(f), cos((double)f)); }
+        if (std::fabs(x) < 89.0) upd(9, wk_cosh_f32((float)x), cosh((double)(float)x));
     }
-    for (int k = 0; k < 9; k++) printf("%.6g\n", worst[k]);
+    for (int k = 0; k < 10; k++) printf("%.6g\n", worst[k]);
     printf("%d\n", (int)(wk_tanh_f64(INFINITY) == 1.0 && wk_tanh_f64(-INFINITY) == -1.0 && wk_tanh_f64(1e-300) == 1e-300
                          && wk_sigmoid_f64(800.0) == 1.0 && wk_sigmoid_f64(-800.0) < 1e-300 && std::isinf(wk_cosh_f64(711.0))
                          && wk_cosh_f64(0.0) == 1.0 && std::isnan(wk_tanh_f64(NAN)) && std::isnan(wk_sigmoid_f64(NAN))
                          && std::signbit(wk_tan_f64(-0.0)) && std::signbit(wk_sin_f64(-0.0)) && wk_cos_f64(0.0) == 1.0
-                         && std::signbit(wk_sin_f32(-0.0f)) && std::signbit(wk_tan_f32(-0.0f)) && wk_cos_f32(0.0f) == 1.0f));
+                         && std::signbit(wk_sin_f32(-0.0f)) && std::signbit(wk_tan_f32(-0.0f)) && wk_cos_f32(0.0f) == 1.0f
+                         && wk_cosh_f32(0.0f) == 1.0f && std::isinf(wk_cosh_f32(89.5f)) && std::isinf(wk_cosh_f32(-INFINITY))
+                         && std::isfinite(wk_cosh_f32(89.4f)) && std::isnan(wk_cosh_f32(NAN))));
     return 0;
 }
 '''
@@ -91,10 +95,10 @@ def test_fast_math_matches_libm(tmp_path):
     r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-o", str(exe), str(cpp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300).stdout.split()
-    worst = [float(v) for v in out[:9]]
+    worst = [float(v) for v in out[:10]]
     e64, e32 = 2.220446049250313e-16, 1.1920928955078125e-07
-    names = ["tanh", "sigmoid", "cosh", "tan", "sin", "cos", "tanf", "sinf", "cosf"]
-    limits = [2 * e64, 2 * e64, 2 * e64, 3 * e64, 2 * e64, 2 * e64, 4 * e32, 2.5 * e32, 2.5 * e32]
+    names = ["tanh", "sigmoid", "cosh", "tan", "sin", "cos", "tanf", "sinf", "cosf", "coshf"]
+    limits = [2 * e64, 2 * e64, 2 * e64, 3 * e64, 2 * e64, 2 * e64, 4 * e32, 2.5 * e32, 2.5 * e32, 2.5 * e32]
     for n, w, lim in zip(names, worst, limits):
         assert w <= lim, (n, w / (e64 if not n.endswith("f") else e32))
-    assert out[9] == "1", "limit / NaN / signed-zero behaviour"
+    assert out[10] == "1", "limit / NaN / signed-zero behaviour"

@@ -242,7 +242,7 @@ __device__ __forceinline__ float wk_cos(float x) { return wk_cos_f32(x); }
 __device__ __forceinline__ double wk_cos(double x) { return wk_cos_f64(x); }
 __device__ __forceinline__ float wk_tan(float x) { return wk_tan_f32(x); }
 __device__ __forceinline__ double wk_tan(double x) { return wk_tan_f64(x); }
-__device__ __forceinline__ float wk_cosh(float x) { return coshf(x); }
+__device__ __forceinline__ float wk_cosh(float x) { return wk_cosh_f32(x); }
 __device__ __forceinline__ double wk_cosh(double x) { return wk_cosh_f64(x); }
 __device__ __forceinline__ float wk_tanh(float x) { return tanhf(x); }
 __device__ __forceinline__ double wk_tanh(double x) { return wk_tanh_f64(x); }
