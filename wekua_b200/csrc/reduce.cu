@@ -1,9 +1,10 @@
 // reduce.cu -- reductions of the hot path: math.sum (src/math/basic.zig:131-203 + kernels/sum.cl), the
 // column sum of Linear.getBiasSensitivity (src/nn/layer/linear.zig:534-577 + bias_step.cl) and the BLAS-style
-// reduction dot named by the north star.  Two-stage, atomic-free and deterministic: stage 1 is a grid-strided
-// 128-bit streaming read with warp-shuffle + shared-memory block reduction into per-block partials, stage 2 a
-// single block folding the partials; the scalar then travels through pinned memory (the reference blocks on a
-// mapped read at the same point, basic.zig:154-171).
+// reduction dot named by the north star.  Deterministic, no floating-point atomics: a grid-strided 128-bit streaming
+// read with warp-shuffle + shared-memory block reduction into per-block partials; for sum / dot the block that arrives
+// last (an integer ticket) folds the partials in index order inside the same launch, for the column sums a second small
+// kernel does.  The scalar of the blocking forms travels through pinned memory, and the host polls a sequence number
+// posted beside it (the reference blocks on a mapped read at the same point, basic.zig:154-171).
 #include <atomic>
 
 #include "common.cuh"
