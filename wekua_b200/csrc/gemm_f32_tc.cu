@@ -118,9 +118,12 @@ template <int CTAS> __device__ __forceinline__ void arrive_on_leader(uint64_t *b
     else mbar_arrive_cluster(bar, 0);
 }
 
-template <int CTAS>
+// PRE: the lo planes were computed by split_lo_kernel beforehand and arrive by TMA next to the raw tiles; the converter warps
+// only relay the barrier (no shared-memory traffic of their own).  Same arithmetic, bit-identical results (split mode 1).
+template <int CTAS, bool PRE>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const Params p) {
     using C = Cfg<CTAS>;
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RAW_BYTES = C::RAW_BYTES, A_BYTES = C::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -137,6 +140,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (PRE) {
+            tma_prefetch_desc(&tmAlo);
+            tma_prefetch_desc(&tmBlo);
+        }
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&bars->raw_full[s], 1);
             mbar_init(&bars->conv_done[s], CONV_WARPS * CTAS);
@@ -172,17 +179,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->stage_free[s], ph ^ 1);
                     uint8_t *a_dst = smem + s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
-                    mbar_arrive_expect_tx(&bars->raw_full[s], RAW_BYTES);
+                    mbar_arrive_expect_tx(&bars->raw_full[s], PRE ? 2 * RAW_BYTES : RAW_BYTES);
                     const int32_t k0 = (int32_t)(kb * BK);
-                    if (p.op_a == 0) {  // A[M][K]: one 32(k) x 128(m) box, K-major
-                        tma_load_2d(a_dst, &tmA, k0, m0, &bars->raw_full[s]);
-                    } else {            // A[K][M]: four 32(m) x 32(k) boxes, MN-major
-                        for (int j = 0; j < BM / 32; j++) tma_load_2d(a_dst + j * 4096, &tmA, m0 + 32 * j, k0, &bars->raw_full[s]);
-                    }
-                    if (p.op_b == 1) {  // B[N][K]: one 32(k) x BN_LOAD(n) box, K-major
-                        tma_load_2d(b_dst, &tmB, k0, n0, &bars->raw_full[s]);
-                    } else {            // B[K][N]: 32(n) x 32(k) boxes, MN-major
-                        for (int j = 0; j < C::BN_LOAD / 32; j++) tma_load_2d(b_dst + j * 4096, &tmB, n0 + 32 * j, k0, &bars->raw_full[s]);
+#pragma unroll
+                    for (int plane = 0; plane < (PRE ? 2 : 1); plane++) {  // raw tiles, then (PRE) the lo tiles RAW_BYTES further on
+                        const CUtensorMap *ma = plane ? &tmAlo : &tmA, *mb = plane ? &tmBlo : &tmB;
+                        uint8_t *ad = a_dst + plane * RAW_BYTES, *bd = b_dst + plane * RAW_BYTES;
+                        if (p.op_a == 0) {  // A[M][K]: one 32(k) x 128(m) box, K-major
+                            tma_load_2d(ad, ma, k0, m0, &bars->raw_full[s]);
+                        } else {            // A[K][M]: four 32(m) x 32(k) boxes, MN-major
+                            for (int j = 0; j < BM / 32; j++) tma_load_2d(ad + j * 4096, ma, m0 + 32 * j, k0, &bars->raw_full[s]);
+                        }
+                        if (p.op_b == 1) {  // B[N][K]: one 32(k) x BN_LOAD(n) box, K-major
+                            tma_load_2d(bd, mb, k0, n0, &bars->raw_full[s]);
+                        } else {            // B[K][N]: 32(n) x 32(k) boxes, MN-major
+                            for (int j = 0; j < C::BN_LOAD / 32; j++) tma_load_2d(bd + j * 4096, mb, n0 + 32 * j, k0, &bars->raw_full[s]);
+                        }
                     }
                 }
             }
@@ -251,6 +263,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&bars->raw_full[s], ph);
+                if (PRE) {  // both planes came by TMA (async proxy -> async proxy): nothing to convert, relay the barrier
+                    __syncwarp();
+                    if (lane == 0) arrive_on_leader<CTAS>(&bars->conv_done[s]);
+                    continue;
+                }
                 float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
                 float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + RAW_BYTES);
 #pragma unroll
@@ -502,6 +519,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// lo plane of a stored operand: lo = rna_tf32(x - trunc_tf32(x)), the converter warps' arithmetic (split mode 1), one pass
+// over HBM.  Rows of `cols` floats at pitch ld (a multiple of 4, 16-byte aligned rows): float4 accesses may run into the
+// row's padding but never past the pitch.
+__global__ void __launch_bounds__(256) split_lo_kernel(const float *__restrict__ x, float *__restrict__ lo, uint64_t rows,
+                                                       uint64_t cols, uint64_t ld) {
+    const uint64_t c4n = (cols + 3) / 4, total = rows * c4n;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (uint64_t)gridDim.x * 256) {
+        const uint64_t r = i / c4n, c = (i - r * c4n) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ld + c));
+        const float xs[4] = {v.x, v.y, v.z, v.w};
+        float ls[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t hb = __float_as_uint(xs[e]) & 0xffffe000u;
+            const float rem = (hb & 0x7f800000u) == 0x7f800000u ? 0.0f : xs[e] - __uint_as_float(hb);
+            uint32_t lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+            ls[e] = __uint_as_float(lb);
+        }
+        *reinterpret_cast<float4 *>(lo + r * ld + c) = make_float4(ls[0], ls[1], ls[2], ls[3]);
+    }
+}
+
 }  // namespace tc
 
 static int env_int(const char *name, int dflt) {
@@ -538,6 +578,33 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed");
         return WK_ERR_CUDA;
     }
+    // WK_GEMM_PRESPLIT=1 (experimental, off by default): lo planes computed in one streaming pass per operand and loaded by
+    // TMA, so the converter warps move no shared memory.  Costs an operand-sized workspace and 2x the L2 -> SM traffic.
+    static const int presplit_env = env_int("WK_GEMM_PRESPLIT", 0);
+    const bool presplit = presplit_env && split_env == 1;
+    CUtensorMap tmAlo = tmA, tmBlo = tmB;
+    if (presplit) {
+        const uint64_t a_rows = op_a ? K : M, a_cols = op_a ? M : K, b_rows = op_b ? N : K, b_cols = op_b ? K : N;
+        const size_t a_bytes = (a_rows * lda * 4 + 255) & ~(size_t)255, b_bytes = b_rows * ldb * 4;
+        if (q->presplit_bytes < a_bytes + b_bytes) {
+            int32_t rc = grow_buffer(q, &q->presplit_ws, &q->presplit_bytes, a_bytes + b_bytes);
+            if (rc != WK_OK) return rc;
+        }
+        float *a_lo = (float *)q->presplit_ws, *b_lo = (float *)((char *)q->presplit_ws + a_bytes);
+        const unsigned grid = (unsigned)q->sm_count * 8;
+        split_lo_kernel<<<grid, 256, 0, q->stream>>>(A, a_lo, a_rows, a_cols, lda);
+        WK_CHECK_LAUNCH();
+        split_lo_kernel<<<grid, 256, 0, q->stream>>>(B, b_lo, b_rows, b_cols, ldb);
+        WK_CHECK_LAUNCH();
+        if (op_a == 0) ok = make_tmap_2d(&tmAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, K, M, lda * 4, BK, BM);
+        else ok = make_tmap_2d(&tmAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, M, K, lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (op_b == 1) ok = ok && make_tmap_2d(&tmBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, K, N, ldb * 4, BK, bn_load);
+        else ok = ok && make_tmap_2d(&tmBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, N, K, ldb * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!ok) {
+            set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed (lo planes)");
+            return WK_ERR_CUDA;
+        }
+    }
 
     Params p{};
     p.C = C;
@@ -559,8 +626,10 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     const uint64_t n_out_tiles = (uint64_t)p.tiles_m * p.tiles_n;
     static bool attr_set[64] = {false};
     if (!attr_set[q->device & 63]) {
-        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
         attr_set[q->device & 63] = true;
     }
     static int max_pairs[64] = {0};  // co-resident CTA pairs (GPCs with an odd SM count strand one SM), per device
@@ -577,7 +646,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         occ.attrs = oa;
         occ.numAttrs = 1;
         int n_cl = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_cl, gemm_tf32x3_kernel<2>, &occ) != cudaSuccess || n_cl <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n_cl, gemm_tf32x3_kernel<2, false>, &occ) != cudaSuccess || n_cl <= 0) {
             cudaGetLastError();
             n_cl = q->sm_count / 2 - 4;
         }
@@ -666,8 +735,13 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1>, tmA, tmB, p));
-        else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2>, tmA, tmB, p));
+        if (presplit) {
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, p));
+        } else {
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, false>, tmA, tmB, tmAlo, tmBlo, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false>, tmA, tmB, tmAlo, tmBlo, p));
+        }
     }
     WK_CHECK_LAUNCH();
     return WK_OK;

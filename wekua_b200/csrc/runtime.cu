@@ -106,6 +106,9 @@ static void queue_fini(wk_queue *q) {
     for (int i = 0; i < q->n_retired; i++) cudaFree(q->retired[i]);
     q->n_retired = 0;
     if (q->splitk_ws) cudaFree(q->splitk_ws);
+    if (q->presplit_ws) cudaFree(q->presplit_ws);
+    q->presplit_ws = nullptr;
+    q->presplit_bytes = 0;
     if (q->splitk_tickets) cudaFree(q->splitk_tickets);
     q->splitk_ws = nullptr;
     q->splitk_tickets = nullptr;
