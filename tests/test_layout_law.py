@@ -57,3 +57,35 @@ def test_one_dimensional_tensors_allocate_twice_their_length():
     assert (t.rows, t.rows_padded, t.row_pitch, t.number_of_elements) == (1, 2, 1 << 20, 2 << 20)
     with pytest.raises(wk.capi.InvalidValue):
         wk.Tensor.empty(ctx, None, (4, 0), np.float32, _external_ptr=0x1000)
+
+
+def _t(ctx, shape, dtype=np.float32):
+    return wk.Tensor.empty(ctx, None, shape, dtype, _external_ptr=0x1000)
+
+
+def test_operator_argument_validation_happens_on_the_host():
+    """gemm.zig:900-941 (InvalidValue / UnqualTensorsContext) and axpy.zig:763-815 (shape mismatch): the host mirror rejects
+    bad arguments before anything is enqueued -- exercised here on tensors that wrap a dummy pointer, pipeline = None"""
+    ctx, other = _FakeContext([[1] * 10]), _FakeContext([[1] * 10])
+    a, b, c = _t(ctx, (6, 10)), _t(ctx, (10, 4)), _t(ctx, (6, 4))
+    bad = [
+        (a, 0, _t(ctx, (9, 4)), 0, c),      # K mismatch
+        (a, 0, b, 0, _t(ctx, (6, 5))),      # C columns
+        (a, 0, b, 0, _t(ctx, (5, 4))),      # C rows
+        (a, 1, b, 0, c),                    # op_a = T makes A [K, M] = [6, 10]: M = 10 != 6
+        (a, 0, b, 1, c),                    # op_b = T makes B [N, K] = [10, 4]: K = 4 != 10
+        (_t(ctx, (2, 6, 10)), 0, b, 0, c),  # not a matrix
+    ]
+    for (x, oa, y, ob, z) in bad:
+        with pytest.raises(wk.capi.InvalidValue):
+            wk.blas.gemm(None, None, x, oa, y, ob, None, z)
+    with pytest.raises(wk.capi.UnqualTensorsContext):
+        wk.blas.gemm(None, None, a, 0, _t(other, (10, 4)), 0, None, c)
+    with pytest.raises(wk.capi.InvalidValue):
+        wk.blas.gemm(None, None, a, 0, _t(ctx, (10, 4), np.float64), 0, None, c)  # dtype mismatch
+    # transposed operands that DO match pass validation (and only then reach the library): checked through the validator
+    wk.blas._validate_gemm(_t(ctx, (10, 6)), _t(ctx, (4, 10)), c, 1, 1)
+    with pytest.raises(wk.capi.WekuaError):
+        wk.blas.axpy(None, _t(ctx, (5,)), 2.0, _t(ctx, (6,)))
+    with pytest.raises(wk.capi.WekuaError):
+        wk.blas.axpy(None, _t(ctx, (2, 3)), 2.0, _t(ctx, (3, 2)))
