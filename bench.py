@@ -45,13 +45,41 @@ FP64_DMMA_PEAK_TFLOPS = 37.04  # profiles/mma_peak_fp64_r01.txt
 # tcgen05.mma kind::tf32, MMA-only loop (operands resident in smem, TMEM accumulators) on this pool's B200,
 # tools/mma_peak_tf32.cu -> profiles/mma_peak_tf32_r01.txt: 900.6-903.2 TF/s over ~3 s (power-capped clock), 1045 burst
 TF32_MMA_PEAK_TFLOPS = {"sustained": 903.2, "burst": 1044.9}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from one `ncu --set full` capture of each kernel on B200
-NCU_TRAFFIC_BYTES = {
-    "gemm_f32_n32768_1gpu": 167.3e9,  # profiles/ncu_gemm_f32_r01c_n32768.txt (algorithmic A+B+C = 12.9e9; the
-    #                                   output-stationary bound for 74 resident 256x256 accumulators is ~150e9)
-    "axpy_f32_2^28": 3.176e9,         # profiles/ncu_axpy_f32_r01.txt (algorithmic 3.221e9)
-    "axpy_f64_2^28": 6.400e9,         # profiles/ncu_axpy_f64_r01.txt (algorithmic 6.442e9)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch: read from the committed `ncu --set full` summaries under
+# profiles/ (tools/ncu_summary.py output), matched by KERNEL NAME so a summary of an older kernel revision is not quoted
+NCU_SUMMARIES = {
+    # key: (profile file, regex the "== <kernel name>" header must match)
+    "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02_n32768.txt", r"gemm_tf32x3_kernel<2, *false>"),
+    "axpy_f32_2^28": ("ncu_axpy_f32_r01.txt", r"map_vec_kernel<float"),
+    "axpy_f64_2^28": ("ncu_axpy_f64_r01.txt", r"map_vec_kernel<double"),
 }
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic_bytes(key):
+    """dram read + write bytes of the first launch in the summary whose kernel name matches; None if there is no such
+    capture in the tree (the roofline then carries traffic = null rather than a stale constant)"""
+    import re
+
+    if key not in NCU_SUMMARIES:
+        return None
+    fname, pat = NCU_SUMMARIES[key]
+    path = os.path.join(ROOT, "profiles", fname)
+    if not os.path.exists(path):
+        return None
+    inside, got = False, {}
+    for line in open(path):
+        if line.startswith("== "):
+            if inside and len(got) == 2:
+                break
+            inside, got = re.search(pat, line) is not None, {}
+            continue
+        if not inside:
+            continue
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in _UNIT:
+            got[f[0]] = float(f[1].replace(",", "")) * _UNIT[f[2]]
+    return sum(got.values()) if len(got) == 2 else None
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -226,20 +254,61 @@ def cpu_reference_axpy(n, dtype, reps=3):
     return 3.0 * n * np.dtype(dtype).itemsize / sec / 1e9
 
 
+def workload_config(N, g, gather):
+    """the `config` object: the SAME for our arm and for --impl reference (the driver compares them)"""
+    return {"workload": f"f32 GEMM NN N={N}, rows of A/C sharded over {g} GPU(s), B replicated "
+                        f"(BASELINE config 5); gather={gather}",
+            "N": N, "parallelism": f"rowshard{g}", "l2": "inputs_exceed_l2"}
+
+
+def host_threads():
+    """Threads the CPU arm may use.  torch.distributed.run exports OMP_NUM_THREADS=1 into every rank; the reference arm
+    is one process on the box's host cores, so that setting is undone BEFORE the OpenMP runtime of the oracle library
+    starts (it reads the variable once, at load)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, n)
+
+
+REF_SAMPLE_SIZES = (8192, 6144, 4096, 3072, 2048, 1024)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.ref_n
-    r = cpu_reference_gemm(n, np.float32, args.steps, max(args.warmup, 1))
-    sample = (f"f32 NN GEMM N={n} (a {n}^3 sub-problem of the N={args.n} workload), restated gemm_pack.cl + "
-              f"gemm_nxn_pack.cl, {r['tile']}x{r['tile']} tiles, vector width {r['vw']}, re-packed every call")
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.pop("OMP_PROC_BIND", None)
+    from oracle import pyoracle as o
+
+    lib = o.lib(fast=True)
+    if hasattr(lib, "wko_set_num_threads"):
+        lib.wko_set_num_threads(threads)
+    # bounded sample: the largest N whose (warmup + steps) calls fit the time budget at the rate a probe call measures,
+    # so the arm ends within about a minute whatever the core count (N = 32768 itself would be ~150 s per call)
+    budget = float(os.environ.get("WK_REF_BUDGET_S", 60.0))
+    warmup = max(args.warmup, 1)
+    probe = cpu_reference_gemm(1024, np.float32, 2, 1)
+    rate = probe["tflops"] * 1e12
+    cands = [c_ for c_ in REF_SAMPLE_SIZES if c_ <= args.ref_n] or [args.ref_n]  # --ref-n caps the sample
+    n = cands[-1]
+    for cand in cands:
+        # big problems run ~1.3x faster per flop than the 1024 probe at best; stay conservative and take the probe rate
+        if (warmup + args.steps) * 2.0 * cand ** 3 / rate <= budget:
+            n = cand
+            break
+    r = cpu_reference_gemm(n, np.float32, args.steps, warmup)
+    sample = (f"f32 NN GEMM N={n} (a {n}^3 sub-problem of the N={args.n} workload, sized to a {budget:.0f} s budget), restated "
+              f"gemm_pack.cl + gemm_nxn_pack.cl, {r['tile']}x{r['tile']} tiles, vector width {r['vw']}, re-packed every call")
+    g = int(os.environ.get("WORLD_SIZE", args.gpus))
     line = {
         "impl": "reference", "metric": "gemm_f32_tflops", "value": r["tflops"], "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_call"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"f32 GEMM NN N={args.n}, rows of A/C sharded over {args.gpus} GPU(s), B replicated "
-                               f"(BASELINE config 5); CPU arm timed on an N={n} sub-problem", "N": args.n, "sample_n": n},
+        "config": workload_config(args.n, g, args.gather if g > 1 else "none"),
         "cpu_baseline": {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["tflops"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -308,7 +377,59 @@ def bench_axpy(wk, ctx, pipe, dtype, n, steps, warmup, peaks, barrier=None, redu
             "config": {"workload": f"{name} axpy, 2^{int(np.log2(n))} elements{per_rank}, alternating x/y (benchmark/axpy.zig)",
                        "l2": "inputs_exceed_l2"},
             "gpu_launches": launches * world,
-            "roofline": hbm_roofline(gbs, peaks, NCU_TRAFFIC_BYTES.get(f"axpy_{name}_2^{int(np.log2(n))}"))}
+            "roofline": hbm_roofline(gbs, peaks, ncu_traffic_bytes(f"axpy_{name}_2^{int(np.log2(n))}"))}
+
+
+def bench_gemm_graph(wk, ctx, pipe, dtype, m, n, k, peaks, reps=20, launches=10):
+    """small problems (BASELINE config 1: 1024^3): `reps` gemm calls captured in one CUDA graph, the graph replayed
+    `launches` times between two events -- kernel time without the host's per-call overhead, as tools/gemm_small_time.py"""
+    a, b, c = (wk.Tensor.alloc(ctx, pipe, s_, dtype) for s_ in ((m, k), (k, n), (m, n)))
+    wk.tensor.random.uniform(pipe, a, 42, -1, 1)
+    wk.tensor.random.uniform(pipe, b, 43, -1, 1)
+    for _ in range(3):
+        wk.blas.gemm(pipe, None, a, 0, b, 0, None, c)
+    pipe.wait_and_cleanup()
+    pipe.begin_capture()
+    for _ in range(reps):
+        wk.blas.gemm(pipe, None, a, 0, b, 0, None, c)
+    graph = pipe.end_capture()
+    for _ in range(3):
+        graph.launch(pipe)
+    pipe.wait_and_cleanup()
+    l0 = wk.capi.launch_count()
+    e0 = ev_record(wk, pipe)
+    for _ in range(launches):
+        graph.launch(pipe)
+    e1 = ev_record(wk, pipe)
+    ms = ev_ms(wk, e0, e1)
+    for e in (e0, e1):
+        wk.capi.lib().wk_event_release(e)
+    graph.release()
+    for t in (a, b, c):
+        t.release(pipe)
+    us = ms * 1e3 / (reps * launches)
+    tf = 2.0 * m * n * k / (us * 1e-6) / 1e12
+    name = "f32" if np.dtype(dtype) == np.float32 else "f64"
+    r = gemm_roofline(tf, name, peaks, sustained=False)
+    r.update({"us_per_call": us, "how": f"{reps} calls per CUDA graph x {launches} replays, L2-resident operands (the problem is 12 MiB)"})
+    return r
+
+
+INT_IMAD_NOTE = ("SIMT integer path: one IMAD per multiply-add; peak = 148 SMs x 128 lanes x 2 op x clock (64 lanes/SM/clk for "
+                 "64-bit IMAD pairs is not modelled; see profiles/sweep_gemm_int_r02.md)")
+
+
+def bench_gemm_int(wk, ctx, pipe, dtype, n, steps, warmup, sm_mhz):
+    """integer GEMM (src/blas/gemm.zig:834-874 for i8..u64; gemm_nxn_gpu.cl:82-319): wrap-around arithmetic, bit-exact.
+    Tera-ops/s = 2 N^3 / t.  i8/u8 run on tcgen05.mma kind::i8 (s32 accumulate in TMEM); wider ints on the SIMT kernel."""
+    a, b, c = (wk.Tensor.alloc(ctx, pipe, (n, n), dtype) for _ in range(3))
+    wk.tensor.random.uniform(pipe, a, 42)
+    wk.tensor.random.uniform(pipe, b, 43)
+    ms, launches, _, _ = timed(wk, pipe, lambda: wk.blas.gemm(pipe, None, a, 0, b, 0, None, c), steps, warmup)
+    for t in (a, b, c):
+        t.release(pipe)
+    tops = 2.0 * n ** 3 * steps / (ms * 1e-3) / 1e12
+    return {"bound": "int-pipe", "achieved": tops, "unit": "Top/s", "ms_per_step": ms / steps, "N": n, "gpu_launches": launches}
 
 
 def bench_gemm_single(wk, ctx, pipe, dtype, n, steps, warmup, peaks, op_a=0, op_b=0):
@@ -325,6 +446,40 @@ def bench_gemm_single(wk, ctx, pipe, dtype, n, steps, warmup, peaks, op_a=0, op_
     return {"metric": f"gemm_{name}_tflops", "value": tf, "unit": "TFLOP/s", "ms_per_step": ms / steps, "dtype": name,
             "config": {"workload": f"{name} GEMM {'NT'[op_a]}{'NT'[op_b]} N={n}, 1 GPU", "l2": "inputs_exceed_l2"},
             "gpu_launches": launches, "roofline": gemm_roofline(tf, name, peaks, sustained=True)}
+
+
+def freivalds_gather_check(wk, ctx, pipe, a_blk, b, c_full, N, rows, row0, rank, world, rowshard):
+    """Every rank proves that the C it holds after the fused all-gather is A.B -- all of it, not only its own rows:
+    for a random sign matrix W [N, 4] it compares C_full.W (from its own gathered copy) with A.(B.W), where the rows of
+    A.(B.W) come from the rank that owns them (exchanged over the host).  A missing, stale or misplaced piece of C of any
+    size changes C.W far beyond the bound.  Bound (per entry): the K-scaled f32 GEMM bound of the parity tests applied
+    to the three products would be too loose to see a lost tile at this size; see the tolerance note below."""
+    rng = np.random.default_rng(99)
+    W = rng.choice(np.array([-1.0, 1.0], dtype=np.float32), size=(N, 4))
+    w = wk.Tensor.alloc(ctx, pipe, (N, 4), np.float32)
+    y = wk.Tensor.alloc(ctx, pipe, (N, 4), np.float32)
+    z = wk.Tensor.alloc(ctx, pipe, (rows, 4), np.float32)
+    t = wk.Tensor.alloc(ctx, pipe, (N, 4), np.float32)
+    wk.tensor.memory.read_from_buffer(pipe, w, W)
+    wk.blas.gemm(pipe, None, b, 0, w, 0, None, y)          # Y = B.W
+    wk.blas.gemm(pipe, None, a_blk, 0, y, 0, None, z)      # my rows of A.Y
+    wk.blas.gemm(pipe, None, c_full, 0, w, 0, None, t)     # C.W from MY copy of the gathered C
+    zh = wk.tensor.memory.to_numpy(pipe, z).astype(np.float64)
+    th = wk.tensor.memory.to_numpy(pipe, t).astype(np.float64)
+    for x in (w, y, z, t):
+        x.release(pipe)
+    z_all = np.concatenate(rowshard.exchange(zh, world), axis=0)  # rank order = row order
+    eps = float(np.finfo(np.float32).eps)
+    # Tolerance: the rounding errors of the three f32 products are independent, so what C.W - A.(B.W) really carries grows
+    # like sqrt(N).eps.|value| (~1e-2 absolute at N = 32768 for values ~3e4; `max_err` in the line is the measurement); 8x that is still 50x smaller than ONE
+    # typical entry of C (|c| ~ sqrt(N/9) = 60), so a single lost 16-byte piece is caught.  (The rigorous worst-case
+    # bound (8N+16).eps.sum|a||b||w| of tests/test_gpu_fullsize.py is ~1e6 here and would let whole tiles through.)
+    bound = 8.0 * np.sqrt(N) * eps * np.abs(z_all).max(axis=0)
+    err = np.abs(th - z_all).max(axis=0)
+    ok = bool(np.all(np.isfinite(th)) and np.all(err <= bound) and float(np.abs(z_all).max()) > 1.0)
+    oks = rowshard.exchange((ok, float(err.max()), float(bound.min())), world)
+    return {"ok": bool(all(o_[0] for o_ in oks)), "method": "Freivalds C.W == A.(B.W), W = 4 sign vectors, every rank's own copy of C",
+            "max_err": max(o_[1] for o_ in oks), "bound": min(o_[2] for o_ in oks)}
 
 
 def run_ours(args):
@@ -434,11 +589,7 @@ def run_ours(args):
         make_step("fused")()
         pipe.wait_and_cleanup()
         barrier()
-        total = float(wk.math.sum(pipe, c_full))
-        blk = float(wk.math.sum(pipe, c_blk))
-        sums = rowshard.exchange((total, blk), world)
-        gather_check = bool(all(s_[0] == sums[0][0] for s_ in sums) and np.isfinite(total)
-                            and abs(sum(s_[1] for s_ in sums) - total) <= 1e-3 * max(1.0, abs(total)))
+        gather_check = freivalds_gather_check(wk, ctx, pipe, a, b, c_full, N, rows, row0, rank, world, rowshard)
 
     # ---------------- e2e: same product through the public API from HOST buffers (pinned), copies inside the region.
     # The user-level recipe for overlap in wekua's model is "several command queues in one context" + event wait lists
@@ -523,7 +674,7 @@ def run_ours(args):
                 for p_ in (p_up, p_push, p_mm, p_dn):
                     p_.wait_and_cleanup()
 
-        e_steps = max(1, min(args.steps, 3))
+        e_steps = max(1, min(args.steps, 10))
         ems, _, _, _ = timed(wk, _All4, e2e_step, e_steps, 1, barrier)
         ems = max_over_ranks(ems)
         for (i_, j_) in ((0, 0), (rows - 1, N - 1), (rows // 2, 17)):  # the product did reach the host
@@ -605,7 +756,7 @@ def run_ours(args):
                 for p_ in (p_up, p_mm, p_dn):
                     p_.wait_and_cleanup()
 
-        e_steps = max(1, min(args.steps, 3))
+        e_steps = max(1, min(args.steps, 10))
         ems, _, _, _ = timed(wk, _All, e2e_step, e_steps, 1, barrier)
         ems = max_over_ranks(ems)
         for (i_, j_) in ((0, 0), (rows - 1, N - 1), (rows // 2, 17)):  # the product did reach the host
@@ -628,12 +779,52 @@ def run_ours(args):
 
     # ---------------- secondary configs + cpu baseline (rank 0, N = 1 only)
     also, cpu = [], None
+    roof_also = {}  # lives INSIDE `roofline` (the driver keeps that object; top-level extras are dropped)
+
+    def keep(key, r_):
+        rf = dict(r_["roofline"])
+        rf.pop("peak_basis", None), rf.pop("bf16_basis", None)
+        rf.update({"ms_per_step": r_["ms_per_step"], "workload": r_["config"]["workload"]})
+        roof_also[key] = rf
+
     if world == 1 and not args.quick:
         s2 = max(3, min(args.steps, 10))
-        also.append(bench_gemm_single(wk, ctx, pipe, np.float32, 16384, s2, 3, peaks))
-        also.append(bench_gemm_single(wk, ctx, pipe, np.float64, 16384 if not args.small else 4096, max(3, s2 // 2), 3, peaks))
-        also.append(bench_axpy(wk, ctx, pipe, np.float32, 1 << 28, 50, 5, peaks))
-        also.append(bench_axpy(wk, ctx, pipe, np.float64, 1 << 28, 50, 5, peaks))
+        for key, dt_, n_, st_ in (("gemm_f32_n16384", np.float32, 16384, s2),
+                                  ("gemm_f64_n16384", np.float64, 16384 if not args.small else 4096, max(3, s2 // 2))):
+            r_ = bench_gemm_single(wk, ctx, pipe, dt_, n_, st_, 3, peaks)
+            also.append(r_)
+            keep(key, r_)
+        for key, dt_ in (("axpy_f32_2p28", np.float32), ("axpy_f64_2p28", np.float64)):
+            r_ = bench_axpy(wk, ctx, pipe, dt_, 1 << 28, 50, 5, peaks)
+            also.append(r_)
+            keep(key, r_)
+        # BASELINE config 1 (the reference's own benchmark size) and a Linear-layer shape, kernel time under a CUDA graph
+        roof_also["gemm_f32_1024"] = bench_gemm_graph(wk, ctx, pipe, np.float32, 1024, 1024, 1024, peaks)
+        roof_also["gemm_f64_1024"] = bench_gemm_graph(wk, ctx, pipe, np.float64, 1024, 1024, 1024, peaks)
+        roof_also["gemm_f32_256x4096x4096"] = bench_gemm_graph(wk, ctx, pipe, np.float32, 256, 4096, 4096, peaks)
+        # BASELINE config 4: transposed operands and alpha/beta at N = 8192 (all four op pairs x (0.75, 0.5))
+        sweep = {}
+        for name_, dt_, st_ in (("f32", np.float32, 10), ("f64", np.float64, 3)):
+            a_, b_, c_ = (wk.Tensor.alloc(ctx, pipe, (8192, 8192), dt_) for _ in range(3))
+            wk.tensor.random.uniform(pipe, a_, 42, -1, 1)
+            wk.tensor.random.uniform(pipe, b_, 43, -1, 1)
+            for opn, oa, ob in (("NN", 0, 0), ("NT", 0, 1), ("TN", 1, 0), ("TT", 1, 1)):
+                wk.tensor.random.uniform(pipe, c_, 44, -1, 1)
+                ms_, _, _, _ = timed(wk, pipe, lambda: wk.blas.gemm(pipe, 0.75, a_, oa, b_, ob, 0.5, c_), st_, 3)
+                tf_ = 2.0 * 8192 ** 3 * st_ / (ms_ * 1e-3) / 1e12
+                sweep[f"{name_}_{opn}"] = round(tf_, 2)
+            for t_ in (a_, b_, c_):
+                t_.release(pipe)
+        pk32, pk64 = TF32_MMA_PEAK_TFLOPS["sustained"] / 3.0, FP64_DMMA_PEAK_TFLOPS
+        roof_also["gemm_n8192_ops_alpha_beta"] = {
+            "bound": "tensor", "unit": "TFLOP/s", "tflops": sweep,
+            "frac_min_f32": min(v for k_, v in sweep.items() if k_.startswith("f32")) / pk32,
+            "frac_min_f64": min(v for k_, v in sweep.items() if k_.startswith("f64")) / pk64,
+            "workload": "C = 0.75 op(A) op(B) + 0.5 C, N = 8192, four transpose pairs (BASELINE config 4)"}
+        # integer GEMM (8 of the 10 real dtypes): i8 on the tensor cores (kind::i8), the rest SIMT
+        clk = (clocks or {}).get("sm_max_mhz") or 1965.0
+        for key, dt_, n_ in (("gemm_i8_n8192", np.int8, 8192), ("gemm_i32_n8192", np.int32, 8192), ("gemm_i64_n4096", np.int64, 4096)):
+            roof_also[key] = bench_gemm_int(wk, ctx, pipe, dt_, n_, 3, 3, clk)
     layer_step = None
     if world == 1 and not args.quick:
         # the other HBM-bound kernels of a layer step, same method as tools/stream_sweep.py:
@@ -648,10 +839,15 @@ def run_ours(args):
                             ctx=ctx, pipe=pipe, reps=10, warm=3, verbose=False)
         layer_step = [{"op": r_["op"], "dtype": r_["dtype"], "bytes_per_elem": r_["bytes_per_elem"], "gbs": round(r_["gbs"], 1),
                        "frac": round(r_["gbs"] / peaks["hbm_gbs"], 3)} for r_ in rows_]
+        roof_also["layer_step_streaming"] = {
+            "bound": "hbm", "unit": "frac of measured copy bandwidth", "n": 1 << 27, "peak": peaks["hbm_gbs"],
+            "frac": {f"{r_['op']}_{r_['dtype']}": r_["frac"] for r_ in layer_step},
+            "frac_min": min(r_["frac"] for r_ in layer_step)}
     if world > 1 and not args.quick:  # "AXPY HBM GB/s at 1/2/4/8 B200": every rank streams its own vectors
-        for dt_ in (np.float32, np.float64):
+        for key, dt_ in (("axpy_f32_2p28", np.float32), ("axpy_f64_2p28", np.float64)):
             r_ = bench_axpy(wk, ctx, pipe, dt_, 1 << 28, 50, 5, peaks, barrier, max_over_ranks, world)
             also.append(r_)
+            keep(key, r_)
     if world == 1 and rank == 0 and not args.no_cpu:
         r = cpu_reference_gemm(args.ref_n, np.float32, 3, 1)
         cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": r["cores"], "kind": "port",
@@ -664,12 +860,11 @@ def run_ours(args):
             "metric": "gemm_f32_tflops", "value": tflops, "unit": "TFLOP/s", "n_gpus": g, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"f32 GEMM NN N={N}, rows of A/C sharded over {g} GPU(s), B replicated "
-                                   f"(BASELINE config 5); gather={gather}",
-                       "N": N, "parallelism": f"rowshard{g}", "l2": "inputs_exceed_l2", "arith": "3xTF32 tcgen05, fp32 accumulate"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True,
-                                      traffic=NCU_TRAFFIC_BYTES["gemm_f32_n32768_1gpu"] if (g == 1 and N == 32768) else None),
+            "config": workload_config(N, g, gather),
+            "arith": "3xTF32 tcgen05, fp32 accumulate", "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {**gemm_roofline(per_gpu_tflops, "f32", peaks, sustained=True,
+                                         traffic=ncu_traffic_bytes("gemm_f32_n32768_1gpu") if (g == 1 and N == 32768) else None),
+                         "also": roof_also},
             "cpu_baseline": cpu, "also": also,
         }
         if layer_step is not None:

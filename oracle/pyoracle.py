@@ -140,6 +140,9 @@ def _bind(lib: C.CDLL) -> C.CDLL:
     lib.wko_xxhash64.restype = C.c_uint64
     lib.wko_xxhash64.argtypes = [C.c_uint64, C.c_uint64]
     lib.wko_num_threads.restype = C.c_int32
+    if hasattr(lib, "wko_set_num_threads"):
+        lib.wko_set_num_threads.restype = None
+        lib.wko_set_num_threads.argtypes = [C.c_int32]
     u64, i32, vp = C.c_uint64, C.c_int32, C.c_void_p
     LP, DP = C.POINTER(Layout), C.POINTER(Device)
     sig = {

@@ -315,6 +315,15 @@ int32_t wko_num_threads(void) {
 #endif
 }
 
+/* timing harness only: launchers such as torch.distributed.run export OMP_NUM_THREADS=1 into their children */
+void wko_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ utils.zig:6-32 */
 void wko_calculate_work_items(const uint64_t *global, uint64_t *local, uint64_t n, uint64_t max_wg) {
     const uint64_t max_per_cu = (uint64_t)pow((double)max_wg, 1.0 / (double)n);

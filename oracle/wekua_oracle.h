@@ -126,6 +126,7 @@ int32_t wko_read_from_buffer(int32_t dtype, void *tensor_buf, const wko_layout *
 int32_t wko_write_to_buffer(int32_t dtype, const void *tensor_buf, const wko_layout *l, void *host);
 
 int32_t wko_num_threads(void);
+void wko_set_num_threads(int32_t n);
 
 #ifdef __cplusplus
 }

@@ -28,3 +28,24 @@ def test_reference_arm_contract_line():
     assert line["value"] > 0 and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_env_uses_all_cores_and_our_config():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 (round 1: the arm then ran on one core and hit the driver's limit);
+    rank 0 must undo that, size its sample to the time budget, and print the SAME config object as our arm; other ranks
+    print nothing"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", WORLD_SIZE="2", RANK="0", LOCAL_RANK="0", WK_REF_BUDGET_S="4")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    ncpu = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == ncpu
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert line["config"] == bench.workload_config(32768, 2, "fused")
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 2
+    assert line["ms_per_step"] * 3 < 4000 * 2  # the sample was sized to the budget
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(env, RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
