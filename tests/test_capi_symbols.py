@@ -67,7 +67,7 @@ def test_host_layout_math_equals_reference_restatement(oracle, dtype):
 
     dev = oracle.device("b200")
     for shape in [(1,), (5,), (10,), (4, 1), (4, 2), (4, 10), (5, 7), (1024, 1024), (2, 3, 4), (3, 5, 7), (2, 3, 4, 5)]:
-        t = Tensor.wrap(_FakeCtx(), None, shape, dtype, device_ptr=0)
+        t = Tensor.empty(_FakeCtx(), None, shape, dtype, _external_ptr=0x1000)
         o = oracle.OTensor(dev, dtype, shape).layout
         assert (t.row_pitch, t.row_pitch_for_vectors, t.slice_pitch, t.number_of_elements, t.number_of_vectors) == \
                (o.row_pitch, o.row_pitch_for_vectors, o.slice_pitch, o.number_of_elements, o.number_of_vectors)
@@ -83,7 +83,7 @@ def test_host_layout_math_complex(oracle):
     dev = oracle.device("b200")
     for dtype in (np.complex64, np.complex128, core.Complex(np.int16)):
         for shape in [(5,), (4, 1), (5, 7), (2, 3, 4)]:
-            t = Tensor.wrap(_FakeCtx(), None, shape, dtype, device_ptr=0)
+            t = Tensor.empty(_FakeCtx(), None, shape, dtype, _external_ptr=0x1000)
             o = oracle.OTensor(dev, dtype, shape).layout
             assert not t.vectors_enabled and t.vector_width == 1
             assert (t.row_pitch, t.slice_pitch, t.number_of_elements) == (o.row_pitch, o.slice_pitch, o.number_of_elements)
@@ -94,15 +94,35 @@ def test_gemm_validation_is_host_side():
     from wekua_b200 import Tensor, blas, capi
 
     ctx = _FakeCtx()
-    a = Tensor.wrap(ctx, None, (4, 5), np.float32, 0)
-    b = Tensor.wrap(ctx, None, (6, 7), np.float32, 0)
-    c = Tensor.wrap(ctx, None, (4, 7), np.float32, 0)
+    a = Tensor.empty(ctx, None, (4, 5), np.float32, _external_ptr=0x1000)
+    b = Tensor.empty(ctx, None, (6, 7), np.float32, _external_ptr=0x1000)
+    c = Tensor.empty(ctx, None, (4, 7), np.float32, _external_ptr=0x1000)
     with pytest.raises(capi.InvalidValue):
         blas.gemm(None, None, a, 0, b, 0, None, c)
     with pytest.raises(capi.UnqualTensorsContext):
-        blas.gemm(None, None, a, 0, Tensor.wrap(_FakeCtx(), None, (5, 7), np.float32, 0), 0, None, c)
+        blas.gemm(None, None, a, 0, Tensor.empty(_FakeCtx(), None, (5, 7), np.float32, _external_ptr=0x1000), 0, None, c)
     pt = blas.PackedTensors.init(None, c, 5, True)
     with pytest.raises(capi.InvalidValue):
         pt.pack(None, a, 0, b, 0)
     with pytest.raises(capi.UnqualTensorsShape):
         blas.axpy(None, a, 1, b)
+
+
+def test_views_describe_only_the_memory_they_were_given():
+    """Tensor.wrap (row / column blocks of a larger matrix): no pad row (it would be the next block's first row), metadata
+    from the pitch the view really has, and whole-buffer ops refuse a view that does not own its flat span"""
+    from wekua_b200 import Tensor, capi, math as wmath
+    from wekua_b200.tensor import fill, memory
+
+    ctx = _FakeCtx()
+    rows_blk = Tensor.wrap(ctx, None, (5, 8), np.float32, 0x1000)               # a row block: odd rows, natural pitch
+    assert rows_blk.is_view and rows_blk.owns_flat_span
+    assert (rows_blk.rows_padded, rows_blk.slice_pitch, rows_blk.number_of_elements, rows_blk.size) == (5, 40, 40, 160)
+    col_blk = Tensor.wrap(ctx, None, (5, 8), np.float32, 0x1000, row_pitch=32)  # a column block of a 32-wide matrix
+    assert col_blk.is_view and not col_blk.owns_flat_span
+    assert (col_blk.row_pitch, col_blk.slice_pitch, col_blk.number_of_elements, col_blk.pitches) == (32, 160, 160, [32, 1])
+    for op in (lambda: wmath.sin(None, col_blk), lambda: memory.padded_to_numpy(None, col_blk)):
+        with pytest.raises(capi.InvalidValue):
+            op()
+    owned = Tensor.empty(ctx, None, (5, 8), np.float32, _external_ptr=0x1000)
+    assert not owned.is_view and owned.rows_padded == 6

@@ -793,7 +793,7 @@ WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void 
     WK_CHECK_QUEUE(q);
     if (!output || !bias) return WK_ERR_INVALID_BUFFER;
     if (row_pitch == 0) return WK_ERR_INVALID_VALUE;
-    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
         constexpr uint64_t VEC = 16 / sizeof(scalar_t);
         const bool vec = aligned16(output) && aligned16(bias) && row_pitch % VEC == 0 && n % VEC == 0;
         const uint64_t n_units = vec ? n / VEC : n, rp_units = vec ? row_pitch / VEC : row_pitch;

@@ -308,7 +308,7 @@ WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *
     WK_CHECK_QUEUE(q);
     if (!sens || !bias_grad) return WK_ERR_INVALID_BUFFER;
     if (n_cols == 0) return WK_ERR_INVALID_VALUE;
-    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+    return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
         constexpr uint64_t VEC = 16 / sizeof(scalar_t);
         // the vector kernel reads whole 128-bit column groups: the last group may reach into the row's padding columns
         const bool vec = aligned16(sens) && row_pitch % VEC == 0 && (n_cols + VEC - 1) / VEC * VEC <= row_pitch;

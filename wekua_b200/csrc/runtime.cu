@@ -35,8 +35,8 @@ int32_t grow_buffer(wk_queue *q, void **buf, size_t *cur_bytes, size_t want_byte
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(q->stream, &st);
         if (st != cudaStreamCaptureStatusNone) q->ever_captured = true;
-        if (q->ever_captured && q->n_retired < 64) {
-            q->retired[q->n_retired++] = *buf;
+        if (q->ever_captured) {
+            q->retired.push_back(*buf);  // never freed under a graph that may still replay; released with the queue
         } else {
             WK_CUDA(cudaStreamSynchronize(q->stream));
             WK_CUDA(cudaFree(*buf));
@@ -64,15 +64,12 @@ int32_t ensure_splitk(wk_queue *q, size_t ws_bytes, size_t n_tickets) {
         int32_t rc = grow_buffer(q, &q->splitk_ws, &q->splitk_ws_bytes, ws_bytes);
         if (rc != WK_OK) return rc;
     }
+    // The tickets are a fixed-capacity array created with the queue and zeroed with a BLOCKING memset there: zeroing them
+    // here on the stream would only be *recorded* when the first split-K GEMM of a queue happens during graph capture, and
+    // an eager launch before the graph's first replay would read uninitialised counters.
     if (q->splitk_n_tickets < n_tickets) {
-        const size_t n = n_tickets < 4096 ? 4096 : n_tickets;
-        size_t cur = q->splitk_n_tickets * sizeof(unsigned);
-        void *t = q->splitk_tickets;
-        int32_t rc = grow_buffer(q, &t, &cur, n * sizeof(unsigned));
-        q->splitk_tickets = (unsigned *)t;
-        q->splitk_n_tickets = rc == WK_OK ? n : 0;
-        if (rc != WK_OK) return rc;
-        WK_CUDA(cudaMemsetAsync(q->splitk_tickets, 0, n * sizeof(unsigned), q->stream));
+        set_error("split-K needs %zu tickets, the queue has %zu", n_tickets, q->splitk_n_tickets);
+        return WK_ERR_INVALID_VALUE;
     }
     return WK_OK;
 }
@@ -95,6 +92,11 @@ static int32_t queue_init(wk_queue *q, int device, int wekua_id, cudaStream_t ad
     memset(q->pinned, 0, 256);
     WK_CUDA(cudaMalloc((void **)&q->reduce_ticket, 64));
     WK_CUDA(cudaMemset(q->reduce_ticket, 0, 64));
+    // split-K tickets: 2 per 128-row block of a split tile (f32) / 1 per tile (f64); split launches never have more work
+    // items than resident CTAs (<= 2 x 148), so 4096 is a hard upper bound with room
+    q->splitk_n_tickets = 4096;
+    WK_CUDA(cudaMalloc((void **)&q->splitk_tickets, q->splitk_n_tickets * sizeof(unsigned)));
+    WK_CUDA(cudaMemset(q->splitk_tickets, 0, q->splitk_n_tickets * sizeof(unsigned)));
     return WK_OK;
 }
 
@@ -103,8 +105,8 @@ static void queue_fini(wk_queue *q) {
     if (q->scratch) cudaFree(q->scratch);
     if (q->ws) cudaFree(q->ws);
     q->ws = nullptr;
-    for (int i = 0; i < q->n_retired; i++) cudaFree(q->retired[i]);
-    q->n_retired = 0;
+    for (void *r : q->retired) cudaFree(r);
+    q->retired.clear();
     if (q->splitk_ws) cudaFree(q->splitk_ws);
     if (q->presplit_ws) cudaFree(q->presplit_ws);
     q->presplit_ws = nullptr;

@@ -58,7 +58,8 @@ def _mean_component(s, n):
 def _unary(name):
     def f(pipeline: Pipeline, tensor: Tensor) -> None:
         # trig.zig:45-51: 1-D over the whole padded buffer
-        capi.check(capi.lib().wk_unary(pipeline.q, tensor.type_index, _OPS[name], tensor.ptr, tensor.number_of_elements))
+        n = tensor.flat_elements(name)
+        capi.check(capi.lib().wk_unary(pipeline.q, tensor.type_index, _OPS[name], tensor.ptr, n))
     f.__name__ = name
     f.__doc__ = f"math.{name}: in place, trig.zig:67-113"
     return f

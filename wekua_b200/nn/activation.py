@@ -29,11 +29,11 @@ class Sigmoid(Activation):
 
     def run(self, pipeline, net_output):
         # sigmoid.zig:62-80: 1-D over the whole padded buffer
-        capi.check(capi.lib().wk_unary(pipeline.q, net_output.type_index, 6, net_output.ptr, net_output.number_of_elements))
+        capi.check(capi.lib().wk_unary(pipeline.q, net_output.type_index, 6, net_output.ptr, net_output.flat_elements("activation")))
 
     def _derivative(self, pipeline, output, derivative):
         capi.check(capi.lib().wk_sigmoid_dev(pipeline.q, output.type_index, output.ptr, derivative.ptr,
-                                             output.number_of_elements))
+                                             output.flat_elements("activation derivative")))
 
 
 class Tanh(Activation):
@@ -44,8 +44,8 @@ class Tanh(Activation):
         return cls()
 
     def run(self, pipeline, net_output):
-        capi.check(capi.lib().wk_unary(pipeline.q, net_output.type_index, 5, net_output.ptr, net_output.number_of_elements))
+        capi.check(capi.lib().wk_unary(pipeline.q, net_output.type_index, 5, net_output.ptr, net_output.flat_elements("activation")))
 
     def _derivative(self, pipeline, output, derivative):
         capi.check(capi.lib().wk_tanh_dev(pipeline.q, output.type_index, output.ptr, derivative.ptr,
-                                          output.number_of_elements))
+                                          output.flat_elements("activation derivative")))

@@ -40,7 +40,10 @@ class Linear:
                  deep: int = 1, enable_bias: bool = True, dtype=np.float32, seed=None, fused: bool = True):
         if n_input == 0 or n_output == 0 or deep == 0:
             raise capi.InvalidValue("InvalidValue")
-        self.context, self.activation, self.bias_enabled, self.dtype, self.fused = context, acti, enable_bias, np.dtype(dtype), fused
+        self.context, self.activation, self.bias_enabled, self.dtype = context, acti, enable_bias, np.dtype(dtype)
+        # the fused epilogue / backward kernels exist for f32 and f64; every other dtype takes the reference's op-by-op
+        # sequence (gemm, bias.cl, bias_step.cl are generic over the real dtypes)
+        self.fused = bool(fused) and self.dtype in (np.dtype(np.float32), np.dtype(np.float64))
         self.weights, self.bias = [], []
         lo, hi = _random_limits(dtype, n_input, n_output)
         w = Tensor.alloc(context, pipeline, (n_output, n_input), dtype)
@@ -109,13 +112,15 @@ class Linear:
     def _add_bias(pipeline, output: Tensor, bias: Tensor):
         """addBias, linear.zig:424-478"""
         capi.check(capi.lib().wk_bias_add(pipeline.q, output.type_index, output.ptr, bias.ptr, output.row_pitch,
-                                          output.number_of_elements))
+                                          output.flat_elements("bias")))
 
     def forward(self, pipeline: Pipeline, input_tensor: Tensor, cache: LinearCache) -> Tensor:
         """linear.zig:480-525: out = act(in . W^T + b) per sub-layer"""
         inp = input_tensor
         for idx, (weight, output, fwd_pt) in enumerate(zip(self.weights, cache.outputs, cache.forward_packed)):
             if self.fused:
+                if inp.dtype != weight.dtype or output.dtype != weight.dtype:  # the check blas.gemm makes
+                    raise capi.UnqualTensorsAttribute("UnqualTensorsAttribute: dtype mismatch")
                 fwd_pt.pack(pipeline, inp, 0, weight, 1)
                 M, N = output.shape
                 capi.check(capi.lib().wk_gemm_bias_act(
@@ -174,7 +179,7 @@ class Linear:
             acti_derivative = cache.acti_derivatives[index]
             if self.fused and self.activation is not None:
                 capi.check(capi.lib().wk_act_backward(pipeline.q, sens.type_index, self.activation.kind, output.ptr,
-                                                      acti_derivative.ptr, sens.ptr, sens.number_of_elements))
+                                                      acti_derivative.ptr, sens.ptr, sens.flat_elements("activation backward")))
             else:
                 if self.activation is not None:
                     self.activation.get_derivative(pipeline, output, acti_derivative)

@@ -17,7 +17,7 @@ def mse(pipeline, output: Tensor, expected: Tensor, cache, calculate_derivative:
         last = cache.slots[-1]
         dev_ptr = last.layer.get_sensitivity(last.cache).ptr
     capi.check(capi.lib().wk_mse(pipeline.q, output.type_index, output.ptr, expected.ptr, err.ptr, dev_ptr,
-                                 output.number_of_elements))
+                                 output.flat_elements("mse")))
     if not want_error:
         return None
     return wmath.mean(pipeline, err)

@@ -40,7 +40,7 @@ def _step_multi(pipeline, kind, records, lr, h0=None, h1=None, h2=None, t=0):
         if x.dtype != dtype:
             raise capi.UnqualTensorsAttribute("UnqualTensorsAttribute: mixed dtypes in one optimizer step")
         arr[i] = capi.OptParam(x.ptr, g.ptr, s0.ptr if s0 is not None else None, s1.ptr if s1 is not None else None,
-                               rec[4] if len(rec) > 4 else x.number_of_elements)
+                               rec[4] if len(rec) > 4 else x.flat_elements("optimizer step"))
     keep = [_scalar(dtype, v) for v in (lr, h0, h1, h2)]
     capi.check(capi.lib().wk_optimizer_step_multi(pipeline.q, records[0][0].type_index, _KIND[kind], arr, len(records),
                                                   keep[0][1], keep[1][1], keep[2][1], keep[3][1], t))
@@ -65,10 +65,18 @@ class Optimizer:
         self._state = {}
 
     def _state_for(self, pipeline, x: Tensor, n: int):
-        st = self._state.get(id(x))
+        """state tensors of parameter `x`, keyed by the parameter's device buffer and validated against its shape / dtype:
+        a Python object id can be recycled by a new tensor after a layer is rebuilt, and would silently inherit stale
+        momentum of possibly another shape"""
+        key = (x.buffer, x.type_index)
+        st = self._state.get(key)
+        if st is not None and (st[0].shape != x.shape or st[0].buffer is None):
+            for t in st:  # the buffer address was reused by a different parameter: start from fresh state
+                t.release(pipeline)
+            st = None
         if st is None:
             st = [Tensor.alloc(x.context, pipeline, x.shape, x.dtype) for _ in range(n)]
-            self._state[id(x)] = st
+            self._state[key] = st
         return st
 
 
@@ -112,7 +120,7 @@ class GDM(Optimizer):
             (v,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
             _b, pb = _scalar(x.dtype, self.beta)
-            capi.check(capi.lib().wk_gdm(pipeline.q, x.type_index, x.ptr, g.ptr, v.ptr, plr, pb, x.number_of_elements))
+            capi.check(capi.lib().wk_gdm(pipeline.q, x.type_index, x.ptr, g.ptr, v.ptr, plr, pb, x.flat_elements("optimizer step")))
 
 
 class Adagrad(Optimizer):
@@ -126,7 +134,7 @@ class Adagrad(Optimizer):
         for x, g in _params(cache):
             (h,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
-            capi.check(capi.lib().wk_adagrad(pipeline.q, x.type_index, x.ptr, g.ptr, h.ptr, plr, x.number_of_elements))
+            capi.check(capi.lib().wk_adagrad(pipeline.q, x.type_index, x.ptr, g.ptr, h.ptr, plr, x.flat_elements("optimizer step")))
 
 
 class RMSProp(Optimizer):
@@ -141,7 +149,7 @@ class RMSProp(Optimizer):
             (h,) = self._state_for(pipeline, x, 1)
             _a, plr = _scalar(x.dtype, self.lr)
             _b, pg = _scalar(x.dtype, self.gamma)
-            capi.check(capi.lib().wk_rmsprop(pipeline.q, x.type_index, x.ptr, g.ptr, h.ptr, plr, pg, x.number_of_elements))
+            capi.check(capi.lib().wk_rmsprop(pipeline.q, x.type_index, x.ptr, g.ptr, h.ptr, plr, pg, x.flat_elements("optimizer step")))
 
 
 class Adam(Optimizer):
@@ -157,4 +165,4 @@ class Adam(Optimizer):
             m, v = self._state_for(pipeline, x, 2)
             sc = [_scalar(x.dtype, s) for s in (self.lr, self.beta1, self.beta2, self.eps)]
             capi.check(capi.lib().wk_adam(pipeline.q, x.type_index, x.ptr, g.ptr, m.ptr, v.ptr, sc[0][1], sc[1][1],
-                                          sc[2][1], sc[3][1], self.t, x.number_of_elements))
+                                          sc[2][1], sc[3][1], self.t, x.flat_elements("optimizer step")))

@@ -90,6 +90,7 @@ class Tensor:
         self.pitches = pitches
         self.size = self.number_of_elements * self.dtype.itemsize
         self._owns = _external_ptr is None
+        self.is_view = False
         if _external_ptr is None:
             p = C.c_void_p()
             capi.check(capi.lib().wk_malloc(pipeline.q, self.size, C.byref(p)))
@@ -109,13 +110,44 @@ class Tensor:
         """view over device memory someone else owns (a row / column block of a larger tensor) with this layout;
         `row_pitch` (elements) overrides the pitch the shape alone would give, for column blocks of a wider matrix"""
         t = cls.empty(context, pipeline, shape, dtype, True, _external_ptr=device_ptr)
+        natural_pitch = t.row_pitch
         if row_pitch is not None:
             if len(t.shape) != 2 or row_pitch < t.shape[1]:
                 raise capi.InvalidValue("InvalidValue: row_pitch override needs a 2-D view and pitch >= cols")
-            t.row_pitch = t.row_pitch_for_vectors = int(row_pitch)
-            t.slice_pitch = t.slice_pitch_for_vectors = t.row_pitch * t.rows_padded
-            t.pitches[0] = t.row_pitch
+            t.row_pitch = int(row_pitch)
+        # A view describes exactly the memory it was given: it owns no pad row (for an odd-row block of a larger matrix
+        # that row is the NEXT block's first row) and its metadata follows the pitch it really has.
+        t.is_view = True
+        t.rows_padded = t.rows
+        t.row_pitch_for_vectors = t.row_pitch // t.vector_width
+        t.slice_pitch = t.row_pitch * t.rows_padded
+        t.slice_pitch_for_vectors = t.slice_pitch // t.vector_width
+        t.number_of_elements = t.slice_pitch * t.depth
+        t.number_of_vectors = t.number_of_elements // t.vector_width
+        t.size = t.number_of_elements * t.dtype.itemsize
+        nd = len(t.shape)
+        if nd >= 2:
+            t.pitches[nd - 2] = t.row_pitch
+        if nd >= 3:
+            t.pitches[nd - 3] = t.slice_pitch
+            for i in range(nd - 4, -1, -1):
+                t.pitches[i] = t.pitches[i + 1] * t.shape[i + 1]
+        # the flat span [buffer, buffer + size) belongs to the view only when its rows are as wide as its pitch allows
+        # (a row block); a column block's span runs through its neighbours' columns
+        t.owns_flat_span = t.row_pitch == natural_pitch
         return t
+
+    def flat_elements(self, what: str) -> int:
+        """number_of_elements for an op that streams over the whole padded buffer (checks that the tensor owns it)"""
+        self.require_flat_span(what)
+        return self.number_of_elements
+
+    def require_flat_span(self, what: str) -> None:
+        """ops that stream over the whole padded buffer (the reference's 1-D launches) are only defined for a
+        tensor that owns that span: column-block views must use the pitched (logical-region) ops"""
+        if self.is_view and not self.owns_flat_span:
+            raise capi.InvalidValue(f"InvalidValue: {what} runs over the whole buffer; this view (pitch {self.row_pitch}, "
+                                    f"{self.cols} columns) does not own it")
 
     def release(self, pipeline: Pipeline) -> None:
         if self.buffer is not None and self._owns:
@@ -176,6 +208,7 @@ class memory:
     @staticmethod
     def padded_to_numpy(pipeline: Pipeline, tensor: Tensor) -> np.ndarray:
         """the whole padded buffer (tests compare padding behaviour with the oracle)"""
+        tensor.require_flat_span("padded_to_numpy")
         out = np.empty(tensor.number_of_elements, dtype=tensor.dtype)
         capi.check(capi.lib().wk_d2h_rect(pipeline.q, _np_ptr(out), tensor.ptr, tensor.size, tensor.size, tensor.size, 1, 1))
         pipeline.wait_and_cleanup()
@@ -186,7 +219,8 @@ class memory:
         """memory.copy, copy.zig:85-98"""
         eql_tensors_shape(src, dst)
         es = src.dtype.itemsize
-        if src.row_pitch == dst.row_pitch and src.slice_pitch == dst.slice_pitch:
+        flat = not (src.is_view and not src.owns_flat_span) and not (dst.is_view and not dst.owns_flat_span)
+        if flat and src.row_pitch == dst.row_pitch and src.slice_pitch == dst.slice_pitch and src.size == dst.size:
             capi.check(capi.lib().wk_d2d(pipeline.q, dst.ptr, src.ptr, src.size))
         else:
             capi.check(capi.lib().wk_d2d_rect(pipeline.q, dst.ptr, dst.row_pitch * es, dst.slice_pitch * es, src.ptr,
@@ -225,7 +259,9 @@ class fill:
 
     @staticmethod
     def zeroes(pipeline: Pipeline, tensor: Tensor) -> None:
-        """fill.zeroes (fill.zig:72-95): the whole padded buffer"""
+        """fill.zeroes (fill.zig:72-95): the whole padded buffer (a column-block view: its logical region)"""
+        if tensor.is_view and not tensor.owns_flat_span:
+            return fill.constant(pipeline, tensor, 0)
         capi.check(capi.lib().wk_memset_zero(pipeline.q, tensor.ptr, tensor.size))
 
 
