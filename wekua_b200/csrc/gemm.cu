@@ -2,7 +2,8 @@
 //
 //   f32  -> 3xTF32 on tcgen05 tensor cores with TMEM accumulators, TMA-fed   (gemm_f32_tc.cu)
 //   f64  -> FP64 tensor-core MMA (DMMA)                                      (gemm_f64_tc.cu)
-//   ints -> SIMT, wrap-around arithmetic, bit-exact                          (gemm_simt.cu)
+//   ints -> tcgen05.mma kind::i8 over byte planes, exact mod 2^bits          (gemm_i8_tc.cu)
+//           small problems: SIMT, wrap-around arithmetic, bit-exact          (gemm_simt.cu)
 // A float problem whose layout cannot feed the tensor-core loaders (pointer / pitch not 16-byte aligned) takes the
 // SIMT kernel as well.  There is no CPU path.
 #include <stdlib.h>
@@ -51,6 +52,20 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
         if (path == 2) {
             set_error("gemm: tensor-core path forced but problem not eligible (alignment)");
             return WK_ERR_INVALID_VALUE;
+        }
+    }
+    if (path != 1 && dtype >= 0 && dtype <= 7 && !bias && act == WK_ACT_NONE && !(peers && peers->n > 1)) {
+        // The byte-plane passes cost W staging/GEMM launches with a fixed ~20 us each: below ~1 G multiply-adds the one-launch
+        // SIMT kernel wins.  WK_GEMM_INT_TC=0 never, =2 always (also what wk_gemm_set_path(2) does).
+        static const int int_tc_env = [] { const char *e = getenv("WK_GEMM_INT_TC"); return e && *e ? atoi(e) : 1; }();
+        const double macs = (double)M * (double)N * (double)K;
+        if (int_tc_env != 0 && (path == 2 || int_tc_env == 2 || macs >= (double)(1ull << 29))) {
+            int32_t rc = gemm_int_tc(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+            if (rc != -1) return rc;
+            if (path == 2) {
+                set_error("gemm: tensor-core path forced but problem not eligible");
+                return WK_ERR_INVALID_VALUE;
+            }
         }
     }
     int32_t rc = gemm_simt(q, dtype, op_a, op_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
