@@ -49,6 +49,10 @@ pub const ERR_TYPE_NOT_SUPPORTED: i32 = 9;
 pub const ERR_NO_DEVICE: i32 = 10;
 pub const ERR_CUDA: i32 = 11;
 
+/// blas.Operation, src/blas/gemm.zig:25-29 (the Zig enum's integer values are passed as they are)
+pub const NO_TRANSPOSE: i32 = 0;
+pub const TRANSPOSE: i32 = 1;
+
 pub const OP_SIN: i32 = 0;
 pub const OP_COS: i32 = 1;
 pub const OP_TAN: i32 = 2;
