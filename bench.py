@@ -49,7 +49,7 @@ TF32_MMA_PEAK_TFLOPS = {"sustained": 903.2, "burst": 1044.9}
 # profiles/ (tools/ncu_summary.py output), matched by KERNEL NAME so a summary of an older kernel revision is not quoted
 NCU_SUMMARIES = {
     # key: (profile file, regex the "== <kernel name>" header must match)
-    "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02_n32768.txt", r"gemm_tf32x3_kernel<2, *false>"),
+    "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02_n32768.txt", r"gemm_tf32x3_kernel<2, *(false|0)>"),
     "axpy_f32_2^28": ("ncu_axpy_f32_r01.txt", r"map_vec_kernel<float"),
     "axpy_f64_2^28": ("ncu_axpy_f64_r01.txt", r"map_vec_kernel<double"),
 }
@@ -415,21 +415,28 @@ def bench_gemm_graph(wk, ctx, pipe, dtype, m, n, k, peaks, reps=20, launches=10)
     return r
 
 
-INT_IMAD_NOTE = ("SIMT integer path: one IMAD per multiply-add; peak = 148 SMs x 128 lanes x 2 op x clock (64 lanes/SM/clk for "
-                 "64-bit IMAD pairs is not modelled; see profiles/sweep_gemm_int_r02.md)")
+# tcgen05.mma kind::i8 (u8 x u8 -> s32), MMA-only loop on this pool's B200: tools/mma_peak_i8.cu -> profiles/mma_peak_i8_r02.txt
+I8_MMA_PEAK_TOPS = {"sustained": 4036.7, "burst": 4534.9}
+BYTE_GEMMS = {1: 1, 2: 3, 4: 10, 8: 36}  # byte-plane products per element product: W (W + 1) / 2
 
 
-def bench_gemm_int(wk, ctx, pipe, dtype, n, steps, warmup, sm_mhz):
-    """integer GEMM (src/blas/gemm.zig:834-874 for i8..u64; gemm_nxn_gpu.cl:82-319): wrap-around arithmetic, bit-exact.
-    Tera-ops/s = 2 N^3 / t.  i8/u8 run on tcgen05.mma kind::i8 (s32 accumulate in TMEM); wider ints on the SIMT kernel."""
+def bench_gemm_int(wk, ctx, pipe, dtype, n, steps, warmup):
+    """integer GEMM (src/blas/gemm.zig:834-874 for i8..u64; gemm_nxn_gpu.cl:82-319): exact mod 2^bits on tcgen05.mma kind::i8
+    over byte planes (csrc/gemm_i8_tc.cu).  Tera-ops/s = 2 N^3 / t of the ELEMENT product; the roofline is the measured
+    kind::i8 MMA ceiling divided by the byte GEMMs one element product costs (1 / 3 / 10 / 36)."""
     a, b, c = (wk.Tensor.alloc(ctx, pipe, (n, n), dtype) for _ in range(3))
     wk.tensor.random.uniform(pipe, a, 42)
     wk.tensor.random.uniform(pipe, b, 43)
-    ms, launches, _, _ = timed(wk, pipe, lambda: wk.blas.gemm(pipe, None, a, 0, b, 0, None, c), steps, warmup)
+    ms, launches, _, _ = timed(wk, pipe, lambda: wk.blas.gemm(pipe, None, a, 0, b, 1, None, c), steps, warmup)
     for t in (a, b, c):
         t.release(pipe)
     tops = 2.0 * n ** 3 * steps / (ms * 1e-3) / 1e12
-    return {"bound": "int-pipe", "achieved": tops, "unit": "Top/s", "ms_per_step": ms / steps, "N": n, "gpu_launches": launches}
+    w = np.dtype(dtype).itemsize
+    peak = I8_MMA_PEAK_TOPS["burst"] / BYTE_GEMMS[w]
+    return {"bound": "tensor", "achieved": tops, "peak": peak, "unit": "Top/s", "frac": tops / peak, "traffic": None,
+            "ms_per_step": ms / steps, "gpu_launches": launches,
+            "workload": f"{np.dtype(dtype).name} GEMM NT N={n}: {BYTE_GEMMS[w]} byte GEMM(s) on tcgen05 kind::i8, bit-exact mod 2^{8 * w}",
+            "peak_basis": f"kind::i8 MMA-only loop burst {I8_MMA_PEAK_TOPS['burst']:.0f} Top/s (profiles/mma_peak_i8_r02.txt) / {BYTE_GEMMS[w]}"}
 
 
 def bench_gemm_single(wk, ctx, pipe, dtype, n, steps, warmup, peaks, op_a=0, op_b=0):
@@ -821,10 +828,10 @@ def run_ours(args):
             "frac_min_f32": min(v for k_, v in sweep.items() if k_.startswith("f32")) / pk32,
             "frac_min_f64": min(v for k_, v in sweep.items() if k_.startswith("f64")) / pk64,
             "workload": "C = 0.75 op(A) op(B) + 0.5 C, N = 8192, four transpose pairs (BASELINE config 4)"}
-        # integer GEMM (8 of the 10 real dtypes): i8 on the tensor cores (kind::i8), the rest SIMT
-        clk = (clocks or {}).get("sm_max_mhz") or 1965.0
-        for key, dt_, n_ in (("gemm_i8_n8192", np.int8, 8192), ("gemm_i32_n8192", np.int32, 8192), ("gemm_i64_n4096", np.int64, 4096)):
-            roof_also[key] = bench_gemm_int(wk, ctx, pipe, dt_, n_, 3, 3, clk)
+        # integer GEMM (8 of the 10 real dtypes): all on the tensor cores (kind::i8 over byte planes)
+        for key, dt_, n_ in (("gemm_i8_n8192", np.int8, 8192), ("gemm_i16_n8192", np.int16, 8192), ("gemm_i32_n8192", np.int32, 8192),
+                             ("gemm_i64_n4096", np.int64, 4096)):
+            roof_also[key] = bench_gemm_int(wk, ctx, pipe, dt_, n_, 5, 3)
     layer_step = None
     if world == 1 and not args.quick:
         # the other HBM-bound kernels of a layer step, same method as tools/stream_sweep.py:
