@@ -25,6 +25,23 @@ static int gemm_path() {
     return g_gemm_path ? g_gemm_path : env;
 }
 
+// Float operands the tensor-core loaders cannot address -- TMA (f32) and 16-byte cp.async (f64) need 16-byte aligned bases
+// and row pitches, and the reference's layout law with vector width 1 gives an f32 tensor of `cols % 4 == 2` columns a
+// pitch of cols floats (src/tensor/main.zig:174-187) -- are first copied into an aligned scratch: one pitched
+// device-to-device copy per operand (2 N^2 bytes against N^3 flops; measured at N = 4098: 37.5 -> see DESIGN.md).
+static int32_t stage_aligned(wk_queue *q, size_t es, const void **ptr, uint64_t *ld, uint64_t rows, uint64_t cols, size_t *offset) {
+    const uint64_t per16 = 16 / es;
+    if (aligned16(*ptr) && *ld % per16 == 0) return WK_OK;
+    const uint64_t new_ld = (cols + per16 - 1) / per16 * per16;
+    char *dst = (char *)q->align_ws + *offset;
+    WK_CUDA(cudaMemcpy2DAsync(dst, new_ld * es, *ptr, *ld * es, cols * es, rows, cudaMemcpyDeviceToDevice, q->stream));
+    count_launch();
+    *offset += ((size_t)rows * new_ld * es + 255) / 256 * 256;
+    *ptr = dst;
+    *ld = new_ld;
+    return WK_OK;
+}
+
 static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K,
                         const void *alpha, const void *A, uint64_t lda, const void *B, uint64_t ldb, const void *beta, void *C,
                         uint64_t ldc, const void *bias, int32_t act, const GemmPeers *peers) {
@@ -43,6 +60,22 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
     }
     const int path = gemm_path();
     if (path != 1 && (dtype == 8 || dtype == 9)) {
+        const size_t es = dtype_size(dtype), per16 = 16 / es;
+        const uint64_t a_rows = op_a ? K : M, b_rows = op_b ? N : K;
+        const bool a_bad = !aligned16(A) || lda % per16, b_bad = !aligned16(B) || ldb % per16;
+        static const int stage_env = [] { const char *e = getenv("WK_GEMM_STAGE_UNALIGNED"); return e && *e ? atoi(e) : 1; }();
+        // (tiny problems -- the XOR network's 4 x 10 x 2 -- are launch-bound either way and keep the one-launch SIMT kernel)
+        if ((a_bad || b_bad) && stage_env && (double)M * (double)N * (double)K >= (double)(1 << 21)) {
+            const size_t need = (a_bad ? ((size_t)a_rows * (a_cols + per16) * es + 256) : 0) + (b_bad ? ((size_t)b_rows * (b_cols + per16) * es + 256) : 0);
+            if (q->align_ws_bytes < need) {
+                int32_t rc = grow_buffer(q, &q->align_ws, &q->align_ws_bytes, need);
+                if (rc != WK_OK) return rc;
+            }
+            size_t off = 0;
+            int32_t rc = stage_aligned(q, es, &A, &lda, a_rows, a_cols, &off);
+            if (rc == WK_OK) rc = stage_aligned(q, es, &B, &ldb, b_rows, b_cols, &off);
+            if (rc != WK_OK) return rc;
+        }
         int32_t rc = dtype == 8
                          ? gemm_f32_tc(q, op_a, op_b, M, N, K, (const float *)alpha, (const float *)A, lda, (const float *)B, ldb,
                                        (const float *)beta, (float *)C, ldc, (const float *)bias, act, peers)

@@ -34,8 +34,9 @@ constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
 constexpr int THREADS = (2 + CONV_WARPS + EPI_WARPS) * 32;  // 448
 constexpr int TMEM_COLS = 512;                               // two 128x256 fp32 accumulators
 constexpr int MAX_STAGES = 3;
-constexpr int EPI_PITCH = 36;                                // floats per row of the epilogue transpose tile (32 + 4)
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;    // 18 KiB
+constexpr int EPI_PITCH = 36;                                // floats per row of the (peer path's) epilogue transpose tile (32 + 4)
+constexpr int EPI_WARP_BYTES = 8192;                         // per epilogue warp: two 32 x 32 fp32 TMA-store staging boxes (swizzled, 4 KiB each)
+constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;        // 32 KiB, 1024-byte aligned (right after the stages)
 
 template <int CTAS> struct Cfg {
     static constexpr int BN_LOAD = BN / CTAS;          // B columns staged by each CTA
@@ -44,7 +45,7 @@ template <int CTAS> struct Cfg {
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;  // hi tiles (TMA lands here)
     static constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // + lo tiles
     static constexpr int STAGES = CTAS == 1 ? 2 : 3;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
 };
 
 struct Params {
@@ -55,6 +56,8 @@ struct Params {
     const float *bias;
     int act;
     int op_a, op_b;
+    int c_vec;  // C rows are 16-byte aligned: 128-bit epilogue accesses
+    int c_tma;  // ... and C has a tensor map: finished 32 x 32 chunks leave through TMA stores
     int split;  // 0: store hi = rna_tf32(x) explicitly; 1: leave x in place, the tensor core truncates; 2: rounds
     uint32_t tiles_m, tiles_n, group_m;
     // split-K (small problems that cannot fill the chip with output tiles): a work item is (tile, split); every split
@@ -68,7 +71,17 @@ struct Params {
     int n_peers, self;
     int peer_bulk;  // fused all-gather: peers receive whole 128-byte row segments as bulk async copies from the staging tile
     float *peers[16];
+    // WK_GEMM_TRACE=1 (debugging aid for launch-bound problems): %globaltimer stamps of the pipeline's milestones, 16 slots per CTA
+    unsigned long long *trace;
 };
+
+__device__ __forceinline__ void trace_stamp(const Params &p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+        p.trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
 
 struct Barriers {
     uint64_t raw_full[MAX_STAGES];    // TMA -> converters                      (own CTA)
@@ -76,6 +89,7 @@ struct Barriers {
     uint64_t stage_free[MAX_STAGES];  // MMA (commit, multicast) -> TMA         (own CTA)
     uint64_t acc_full[2];             // MMA (commit, multicast) -> epilogue    (own CTA)
     uint64_t acc_empty[2];            // epilogue of both CTAs -> MMA           (leader CTA's copy is used)
+    uint64_t fold_full;               // split-K: the other splits' partials of my chunks have landed in shared memory
     uint32_t tmem_base;
 };
 
@@ -113,6 +127,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// out of line: the activation's libdevice code (expf, tanhf) would otherwise be inlined at every unrolled epilogue position and
+// push the hot store path out of the instruction cache
+// (by value: an array passed by reference would force the caller's registers into local memory)
+__device__ __noinline__ float apply_act1(float v, int act) { return apply_act(v, act); }
+__device__ __noinline__ float4 apply_act4(float4 v, int act) {
+    return make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
+}
+
 template <int CTAS> __device__ __forceinline__ void arrive_on_leader(uint64_t *bar) {
     if (CTAS == 1) mbar_arrive(bar);
     else mbar_arrive_cluster(bar, 0);
@@ -123,19 +145,21 @@ template <int CTAS> __device__ __forceinline__ void arrive_on_leader(uint64_t *b
 template <int CTAS, bool PRE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const Params p) {
+                   const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+                   const __grid_constant__ CUtensorMap tmC, const Params p) {
     using C = Cfg<CTAS>;
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RAW_BYTES = C::RAW_BYTES, A_BYTES = C::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic smem base has the same CTA-relative offset in both CTAs of a pair, so the aligned tiles do too
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * STAGE_BYTES);
+    Barriers *bars = reinterpret_cast<Barriers *>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 1 ? 0u : cluster_ctarank();
     const uint32_t unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;  // a unit = one CTA or one CTA pair
     const uint32_t num_tiles = p.n_full + (p.tiles_m * p.tiles_n - p.n_full) * p.splits;  // work items: tiles, then (tail tile, split)
     const uint32_t num_kb = (uint32_t)((p.K + BK - 1) / BK);
+    if (threadIdx.x == 0) trace_stamp(p, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -153,6 +177,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(&bars->acc_full[a], 1);
             mbar_init(&bars->acc_empty[a], EPI_WARPS * CTAS);
         }
+        mbar_init(&bars->fold_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -164,6 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     else cluster_sync_all();  // the peer's barriers must be initialised before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    if (threadIdx.x == 0) trace_stamp(p, 1);
 
     if (warp == 0) {
         // ================================================================= TMA producer (every CTA, own operand halves)
@@ -196,6 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             for (int j = 0; j < C::BN_LOAD / 32; j++) tma_load_2d(bd + j * 4096, mb, n0 + 32 * j, k0, &bars->raw_full[s]);
                         }
                     }
+                    if (it == 0) trace_stamp(p, 2);
                 }
             }
         }
@@ -222,6 +249,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->conv_done[s], ph);
                     tc_fence_after();
+                    if (it == 0 && lane == 0) trace_stamp(p, 4);
                     if (elect_one()) {
                         const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), b_hi = a_hi + A_BYTES;
                         const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = b_hi + RAW_BYTES;
@@ -250,6 +278,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                     __syncwarp();
                 }
+                if (lane == 0) trace_stamp(p, 5);
             }
         }
     } else if (warp < 2 + CONV_WARPS) {
@@ -263,6 +292,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&bars->raw_full[s], ph);
+                if (it == 0 && ct == 0) trace_stamp(p, 3);
                 if (PRE) {  // both planes came by TMA (async proxy -> async proxy): nothing to convert, relay the barrier
                     __syncwarp();
                     if (lane == 0) arrive_on_leader<CTAS>(&bars->conv_done[s]);
@@ -300,9 +330,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ================================================================= epilogue (every CTA: its 128 rows x 256 columns)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        float *epi = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256) + q * 32 * EPI_PITCH;
+        uint8_t *const epi_raw = smem + STAGES * STAGE_BYTES + q * EPI_WARP_BYTES;  // 1024-byte aligned
+        float *epi = reinterpret_cast<float *>(epi_raw);
         uint32_t tile_i = 0;
-        const bool vec_ok = (p.ldc % 4 == 0);
+        const bool vec_ok = p.c_vec != 0;
         for (uint32_t w = unit; w < num_tiles; w += n_units, tile_i++) {
             uint32_t t, sp, kb0, kb1, tm, tn;
             work_coords(p, w, num_kb, t, sp, kb0, kb1);
@@ -310,6 +341,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
             mbar_wait(&bars->acc_full[acc], acc_ph);
             tc_fence_after();
+            if (q == 0 && lane == 0) trace_stamp(p, 6);
             const uint64_t row0 = (uint64_t)(tm * CTAS + rank) * BM + q * 32;
             const uint64_t col0 = (uint64_t)tn * BN;
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
@@ -349,11 +381,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const float4 bv = *reinterpret_cast<const float4 *>(p.bias + col);
                             v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
                         }
-                        if (p.act) {
-#pragma unroll
-                            for (int e = 0; e < 4; e++) v[e] = apply_act(v[e], p.act);
-                        }
-                        const float4 out = make_float4(v[0], v[1], v[2], v[3]);
+                        float4 out = make_float4(v[0], v[1], v[2], v[3]);
+                        if (p.act) out = apply_act4(out, p.act);
                         *reinterpret_cast<float4 *>(cp) = out;
                         if (p.peer_bulk) {  // the finished values go back into the staging tile; the copy engine ships them
                             *reinterpret_cast<float4 *>(epi + rl * EPI_PITCH + (lane & 7) * 4) = out;
@@ -368,7 +397,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 float o = v[e];
                                 if (p.has_beta) o += p.beta * cp[e];
                                 if (p.bias) o += p.bias[col + e];
-                                o = apply_act(o, p.act);
+                                if (p.act) o = apply_act1(o, p.act);
                                 cp[e] = o;
                                 for (int pi = 0; pi < p.n_peers; pi++)
                                     if (pi != p.self) p.peers[pi][row * p.ldc + col + e] = o;
@@ -400,54 +429,213 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();  // the tile is overwritten by the next chunk
             };
 
-            if (p.splits == 1 || w < p.n_full) {
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c * 32, r);
-                    tmem_ld_wait();
-                    if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+            // Local-only stores (no peer GPUs): every lane writes ITS row of the chunk -- one whole 128-byte line -- straight from
+            // the registers tcgen05.ld filled.  The epilogue runs ONE warp per scheduler, so it is bound by instruction latency:
+            // the transposing path above costs ~1200 dependent instructions per chunk and warp (2.5 us: 20 us per tile, measured
+            // with WK_GEMM_TRACE), this one ~60.  The partial lines a warp instruction leaves are merged in L2 before write-back.
+            float *my_c = p.C + (row0 + lane) * p.ldc + col0;
+            asm volatile("" : "+l"(my_c));  // (not rematerialised from row * ldc at every use)
+            const bool my_row_ok = row0 + lane < p.M;
+            auto store_rows = [&](const uint32_t (&r)[32], int c) {
+                const uint64_t col = col0 + (uint64_t)c * 32;
+                if (!my_row_ok || col >= p.N) return;
+                float *cp = my_c + c * 32;
+                asm volatile("" : "+l"(cp));  // keep the row pointer in a register pair: the 8 accesses below are [cp + imm]
+                if (vec_ok && col + 32 <= p.N) {
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
+                                               __uint_as_float(r[g * 4 + 3]));
+                        if (p.has_alpha) {
+                            v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+                        }
+                        if (p.has_beta) {
+                            const float4 o = *reinterpret_cast<const float4 *>(cp + g * 4);
+                            v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+                        }
+                        if (p.bias) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(p.bias + col + g * 4);
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if (p.act) v = apply_act4(v, p.act);
+                        *reinterpret_cast<float4 *>(cp + g * 4) = v;
                     }
-                    store_chunk(r, c);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {  // fully unrolled: a dynamic index would put r[] in local memory
+                        if (col + e < p.N) {
+                            float o = __uint_as_float(r[e]);
+                            if (p.has_alpha) o *= p.alpha;
+                            if (p.has_beta) o += p.beta * cp[e];
+                            if (p.bias) o += p.bias[col + e];
+                            cp[e] = p.act ? apply_act1(o, p.act) : o;
+                        }
+                    }
                 }
-            } else {
-                // split-K: park this split's raw partial of this CTA's 128 x 256 block in the workspace, in register
-                // order -- float4 index ((c * 8 + g) * 128 + thread) -- so every warp access covers 512 contiguous bytes
-                // and any CTA of the tile can fold any 32-column chunk with the same (warp, lane) -> row mapping
-                const uint64_t half = (uint64_t)(t - p.n_full) * CTAS + rank;  // which 128-row block of which split tile
-                const int et = q * 32 + lane;                     // 0..127: row of the block
-                constexpr uint64_t PART_F4 = (uint64_t)BM * BN / 4;
-                float4 *mine = reinterpret_cast<float4 *>(p.ws) + (half * p.splits + sp) * PART_F4 + et;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c * 32, r);
-                    tmem_ld_wait();
-                    if (c == BN / 32 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
-                    }
+            };
+            // TMA-store path (C has a tensor map, no beta, no peers): the lane puts its row of the chunk into a 128-byte-swizzled
+            // 32 x 32 staging box (16-byte piece g of row r at piece g ^ (r & 7): conflict-free) and ONE thread hands the box to
+            // the TMA engine, which clips it against C's bounds.  ~40 instructions per chunk and warp, and the global write is
+            // asynchronous: two boxes per warp alternate, a box is reused once its previous store has finished READING it.
+            // Everything the chunk loop needs is pinned in registers first: with ONE warp per scheduler the epilogue is bound by
+            // instruction latency, and a constant-bank read or an address re-derivation in front of every store (what the compiler
+            // emits when it may rematerialise) costs 20-40 cycles each -- measured 0.64 us per chunk against 0.1 us like this.
+            uint32_t box_lane = smem_u32(epi_raw) + lane * 128;      // this lane's row in staging box 0
+            uint32_t swz = (uint32_t)(lane & 7) << 4;                // 16-byte piece g sits at piece g ^ (row & 7)
+            uint64_t tmc_addr = reinterpret_cast<uint64_t>(&tmC);
+            int f_alpha = p.has_alpha, f_act = p.act;
+            float alpha_v = p.alpha;
+            const float *bias_p = p.bias;
+            asm volatile("" : "+r"(box_lane), "+r"(swz), "+l"(tmc_addr), "+r"(f_alpha), "+r"(f_act), "+f"(alpha_v), "+l"(bias_p));
+            const bool plain = !f_alpha && !f_act && bias_p == nullptr;
+            auto store_tma = [&](const uint32_t (&r)[32], int c, int n_chunk) {
+                const uint32_t box = box_lane + (n_chunk & 1) * 4096;
+                const bool tr = p.trace && c == 1 && q == 0 && lane == 0;
+                if (tr) trace_stamp(p, 12);
+                if (n_chunk >= 2) {  // the store issued two chunks ago has read this box
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+                if (plain) {
 #pragma unroll
                     for (int g = 0; g < 8; g++)
-                        __stcg(mine + (c * 8 + g) * 128, make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
-                                                                     __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (((uint32_t)g << 4) ^ swz)), "r"(r[g * 4]),
+                                     "r"(r[g * 4 + 1]), "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3])
+                                     : "memory");
+                } else {
+                    const uint64_t col = col0 + (uint64_t)c * 32;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
+                                               __uint_as_float(r[g * 4 + 3]));
+                        if (f_alpha) {
+                            v.x *= alpha_v; v.y *= alpha_v; v.z *= alpha_v; v.w *= alpha_v;
+                        }
+                        if (bias_p) {
+                            if (col + g * 4 + 4 <= p.N) {
+                                const float4 bv = *reinterpret_cast<const float4 *>(bias_p + col + g * 4);
+                                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            } else {  // ragged right edge: the store clips these columns, the bias read must not run past N
+                                if (col + g * 4 + 0 < p.N) v.x += bias_p[col + g * 4 + 0];
+                                if (col + g * 4 + 1 < p.N) v.y += bias_p[col + g * 4 + 1];
+                                if (col + g * 4 + 2 < p.N) v.z += bias_p[col + g * 4 + 2];
+                            }
+                        }
+                        if (f_act) v = apply_act4(v, f_act);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(box + (((uint32_t)g << 4) ^ swz)), "f"(v.x), "f"(v.y),
+                                     "f"(v.z), "f"(v.w)
+                                     : "memory");
+                    }
                 }
-                // publish, count the arrival, and wait for the other splits of the tile: all of them are resident (one
-                // work item per unit, host-checked), so this is a short spin, not a scheduling dependency
-                unsigned *arrived = p.tickets + 2 * half, *done = arrived + 1;
-                __threadfence();
+                if (tr) trace_stamp(p, 13);
+                fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (tr) trace_stamp(p, 14);
+                if (lane == 0) {
+                    const int32_t ccol = (int32_t)(col0 + (uint64_t)c * 32), crow = (int32_t)row0;
+                    if ((uint64_t)ccol < p.N && row0 < p.M)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmc_addr),
+                                     "r"(ccol), "r"(crow), "r"(box - lane * 128)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (tr) trace_stamp(p, 15);
+            };
+            const bool local_only = p.n_peers == 0;
+            const bool use_tma_store = local_only && p.c_tma && !p.has_beta;
+            int n_chunk = 0;
+
+            if (p.splits == 1 || w < p.n_full) {
+                if (use_tma_store) {
+                    // two register buffers: the TMEM load of chunk c + 1 is in flight while chunk c is staged and stored
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+                        if (c == 0 && q == 0 && lane == 0) trace_stamp(p, 9);
+                        store_tma(ra, c, n_chunk++);
+                        if (q == 0 && lane == 0 && c == 0) trace_stamp(p, 10);
+                        tmem_ld_wait();
+                        if (c + 2 < BN / 32) {
+                            tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                        } else {  // accumulator fully read: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+                        }
+                        store_tma(rb, c + 1, n_chunk++);
+                        if (q == 0 && lane == 0 && c == 2) trace_stamp(p, 11);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; c++) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c * 32, r);
+                        tmem_ld_wait();
+                        if (c == BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+                        }
+                        if (local_only) store_rows(r, c);
+                        else store_chunk(r, c);
+                    }
+                }
+            } else {
+                // split-K: every split of the tile folds ITS share of the tile's 32-column chunks (c = sp, sp + splits, ...).  The
+                // chunks the OTHER splits fold are parked in the workspace in register order -- float4 index
+                // ((c * 8 + g) * 128 + thread): every warp access covers 512 contiguous bytes and any CTA of the tile reads a
+                // chunk back with the same (warp, lane) -> row mapping; a split's own chunks stay in its TMEM accumulator.
+                const uint64_t half = (uint64_t)(t - p.n_full) * CTAS + rank;  // which 128-row block of which split tile
+                const int et = q * 32 + lane;                                  // 0..127: row of the block
+                constexpr uint64_t PART_F4 = (uint64_t)BM * BN / 4;
+                uint32_t splits = p.splits;
+                float4 *mine = reinterpret_cast<float4 *>(p.ws) + (half * splits + sp) * PART_F4 + et;
+                const float4 *part0 = reinterpret_cast<const float4 *>(p.ws) + half * splits * PART_F4 + et;
+                unsigned *arrived = p.tickets + 2 * half;
+                asm volatile("" : "+l"(mine), "+l"(part0), "+l"(arrived), "+r"(splits));  // pinned: see store_tma
+                auto next_parked = [&](uint32_t c) {  // next chunk >= c that another split folds
+                    while (c < BN / 32 && c % splits == sp) c++;
+                    return c;
+                };
+                auto park = [&](const uint32_t (&r)[32], uint32_t c) {
+                    float4 *mc = mine + c * (8 * 128);
+#pragma unroll
+                    for (int g = 0; g < 8; g++)
+                        __stcg(mc + g * 128, make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                         __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])));
+                };
+                {  // two register buffers: the TMEM load of the next chunk is in flight while this one is written out
+                    uint32_t ra[32], rb[32];
+                    uint32_t ca = next_parked(0), cb;
+                    if (ca < BN / 32) tmem_ld_32x32(taddr + ca * 32, ra);
+#pragma unroll 1
+                    while (ca < BN / 32) {
+                        tmem_ld_wait();
+                        cb = next_parked(ca + 1);
+                        if (cb < BN / 32) tmem_ld_32x32(taddr + cb * 32, rb);
+                        park(ra, ca);
+                        if (cb >= BN / 32) break;
+                        tmem_ld_wait();
+                        ca = next_parked(cb + 1);
+                        if (ca < BN / 32) tmem_ld_32x32(taddr + ca * 32, ra);
+                        park(rb, cb);
+                    }
+                }
+                if (q == 0 && lane == 0) trace_stamp(p, 9);
+                // publish and wait for the other splits of the tile: all of them are resident (one work item per unit,
+                // host-checked), so this is a short spin, not a scheduling dependency.  ONE thread releases for the whole
+                // warpgroup (the CTA barrier orders everybody's stores before its release: cumulativity) and acquires for it.
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
                 if (threadIdx.x == (2 + CONV_WARPS) * 32) {
-                    atomicAdd(arrived, 1u);
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(arrived) : "memory");
                     unsigned seen;
                     long long t0 = 0;
                     for (uint32_t spins = 0;; spins++) {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrived) : "memory");
-                        if (seen >= p.splits) break;
+                        if (seen >= splits) break;
                         if (spins > 4096) {  // bounded like mbar_wait: a protocol bug traps instead of hanging the GPU
                             if (t0 == 0) t0 = clock64();
                             else if (clock64() - t0 > 6000000000LL) __trap();
@@ -455,46 +643,61 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-                __threadfence();
-                // every split folds its share of the 32-column chunks (c = sp, sp + splits, ...), partials added in split
-                // order 0..splits-1 whoever does it: deterministic.  Half a chunk at a time, four splits' loads in flight.
-                const float4 *part0 = reinterpret_cast<const float4 *>(p.ws) + half * p.splits * PART_F4 + et;
+                if (q == 0 && lane == 0) trace_stamp(p, 10);
+                // fold: the own partial (from TMEM) first, then the other splits' in ascending order.  Which split folds a chunk
+                // is a function of the chunk alone, so the summation order -- and every bit of C -- is the same on every launch.
+                // The other splits' partials of my chunks (16 KiB each, contiguous) are fetched by the bulk-copy engine into the
+                // pipeline's stage memory, idle now that the accumulator is complete: one thread issues <= 12 copies, everybody
+                // waits once and folds from shared memory instead of paying an L2 round trip per half chunk.
+                const uint32_t n_mine = (BN / 32 - sp + splits - 1) / splits;  // chunks sp, sp + splits, ...
+                if (threadIdx.x == (2 + CONV_WARPS) * 32) {
+                    fence_proxy_async_all();  // the partials were written (and acquired) through the generic proxy; the copy engine reads them
+                    mbar_arrive_expect_tx(&bars->fold_full, n_mine * (splits - 1) * 16384u);
+                    uint32_t slot = 0;
+                    for (uint32_t c = sp; c < BN / 32; c += splits)
+                        for (uint32_t s2 = 0; s2 < splits; s2++) {
+                            if (s2 == sp) continue;
+                            const float4 *src = part0 - et + (uint64_t)s2 * PART_F4 + c * (8 * 128);
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                             smem_u32(smem + slot * 16384)),
+                                         "l"(src), "r"(16384u), "r"(smem_u32(&bars->fold_full))
+                                         : "memory");
+                            slot++;
+                        }
+                }
+                mbar_wait(&bars->fold_full, 0);
+                {
+                    uint32_t slot = 0;
 #pragma unroll 1
-                for (int c = (int)sp; c < BN / 32; c += (int)p.splits) {
-                    uint32_t r[32];
-#pragma unroll
-                    for (int hc = 0; hc < 2; hc++) {
-                        float4 acc4[4];
+                    for (uint32_t c = sp; c < BN / 32; c += splits) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c * 32, r);
+                        tmem_ld_wait();
 #pragma unroll 1
-                        for (uint32_t sb = 0; sb < p.splits; sb += 4) {  // groups of 4 splits: 16 loads in flight per thread
-                            float4 v[4][4];
+                        for (uint32_t s2 = 0; s2 < splits; s2++) {
+                            if (s2 == sp) continue;
+                            const float4 *ps = reinterpret_cast<const float4 *>(smem + slot * 16384) + et;
+                            slot++;
 #pragma unroll
-                            for (int s2 = 0; s2 < 4; s2++)
-#pragma unroll
-                                for (int g = 0; g < 4; g++)
-                                    if (sb + s2 < p.splits)
-                                        v[s2][g] = __ldcg(part0 + (uint64_t)(sb + s2) * PART_F4 + (c * 8 + hc * 4 + g) * 128);
-#pragma unroll
-                            for (int g = 0; g < 4; g++) {
-                                float4 a4 = sb == 0 ? v[0][g] : acc4[g];
-#pragma unroll
-                                for (int s2 = 0; s2 < 4; s2++)
-                                    if ((sb != 0 || s2 != 0) && sb + s2 < p.splits) {
-                                        a4.x += v[s2][g].x; a4.y += v[s2][g].y; a4.z += v[s2][g].z; a4.w += v[s2][g].w;
-                                    }
-                                acc4[g] = a4;
+                            for (int g = 0; g < 8; g++) {
+                                const float4 v = ps[g * 128];
+                                r[g * 4] = __float_as_uint(__uint_as_float(r[g * 4]) + v.x);
+                                r[g * 4 + 1] = __float_as_uint(__uint_as_float(r[g * 4 + 1]) + v.y);
+                                r[g * 4 + 2] = __float_as_uint(__uint_as_float(r[g * 4 + 2]) + v.z);
+                                r[g * 4 + 3] = __float_as_uint(__uint_as_float(r[g * 4 + 3]) + v.w);
                             }
                         }
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            r[(hc * 4 + g) * 4] = __float_as_uint(acc4[g].x);
-                            r[(hc * 4 + g) * 4 + 1] = __float_as_uint(acc4[g].y);
-                            r[(hc * 4 + g) * 4 + 2] = __float_as_uint(acc4[g].z);
-                            r[(hc * 4 + g) * 4 + 3] = __float_as_uint(acc4[g].w);
-                        }
+                        if (use_tma_store) store_tma(r, (int)c, n_chunk++);
+                        else if (local_only) store_rows(r, (int)c);
+                        else store_chunk(r, (int)c);
+                        if (q == 0 && lane == 0 && c == sp) trace_stamp(p, 11);
                     }
-                    store_chunk(r, c);
                 }
+                // accumulator fully read: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_on_leader<CTAS>(&bars->acc_empty[acc]);
+                unsigned *done = arrived + 1;
                 // the last split to finish re-arms the counters for the next launch
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
                 if (threadIdx.x == (2 + CONV_WARPS) * 32) {
@@ -505,13 +708,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
-        // bulk copies to the peers: complete (written, not only read) before this CTA is allowed to finish
-        if (p.peer_bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // bulk copies to the peers / TMA stores of C: complete (written, not only read) before this CTA is allowed to finish
+        if (p.peer_bulk || p.c_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (q == 0 && lane == 0) trace_stamp(p, 7);
     }
 
     tc_fence_before();
     if (CTAS == 1) __syncthreads();
     else cluster_sync_all();  // no CTA of a pair may exit (or free TMEM) while its partner can still touch it
+    if (threadIdx.x == 0) trace_stamp(p, 8);
     if (warp == 1) {
         tc_fence_after();
         if (CTAS == 1) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -554,7 +759,8 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
                     const float *bias, int32_t act, const GemmPeers *peers) {
     using namespace tc;
     // TMA needs 16-byte aligned bases and pitches; the epilogue wants 16-byte aligned C rows
-    if (!aligned16(A) || !aligned16(B) || !aligned16(C) || (lda % 4) || (ldb % 4) || (ldc % 4)) return -1;
+    // (gemm.cu stages unaligned A / B into an aligned scratch first; an unaligned C takes the epilogue's element-wise stores)
+    if (!aligned16(A) || !aligned16(B) || (lda % 4) || (ldb % 4)) return -1;
     if (bias && !aligned16(bias)) return -1;
     if (q->prop.major != 10) return -1;
     if (M > 0x7fffffffULL || N > 0x7fffffffULL || K > 0x7fffffffULL) return -1;
@@ -609,6 +815,14 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     Params p{};
     p.C = C;
     p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+    p.c_vec = aligned16(C) && ldc % 4 == 0;
+    static const int tma_store_env = env_int("WK_GEMM_TMA_STORE", 1);
+    CUtensorMap tmC = tmA;
+    p.c_tma = 0;
+    if (p.c_vec && tma_store_env && !(peers && peers->n > 1)) {
+        // finished 32 x 32 chunks of C: 128-byte rows, swizzled staging box, clipped against [M, N] by the engine
+        p.c_tma = make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, N, M, ldc * 4, 32, 32) ? 1 : 0;
+    }
     p.has_alpha = (alpha != nullptr || beta != nullptr);
     p.has_beta = (beta != nullptr);
     p.alpha = alpha ? *alpha : 1.0f;
@@ -702,9 +916,17 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         p.self = peers->self;
         for (int i = 0; i < peers->n; i++) p.peers[i] = (float *)peers->ptrs[i];
         static const int bulk_env = env_int("WK_GEMM_PEER_BULK", 1);
-        p.peer_bulk = bulk_env && peers->n > 1 && N % 4 == 0;  // whole 16-byte pieces per row segment
+        p.peer_bulk = bulk_env && peers->n > 1 && N % 4 == 0 && p.c_vec;  // whole 16-byte pieces per row segment
     }
 
+    static const int trace_env = env_int("WK_GEMM_TRACE", 0);
+    static unsigned long long *trace_buf = nullptr;
+    p.trace = nullptr;
+    if (trace_env) {
+        if (!trace_buf) WK_CUDA(cudaMalloc((void **)&trace_buf, 512 * 16 * sizeof(unsigned long long)));
+        WK_CUDA(cudaMemsetAsync(trace_buf, 0, 512 * 16 * sizeof(unsigned long long), q->stream));
+        p.trace = trace_buf;
+    }
     const uint64_t num_tiles = n_full + n_split_tiles * p.splits;
     // split launches are cooperative: the grid must be what can be resident at once
     const uint64_t max_units = p.splits > 1 ? units_avail : (uint64_t)q->sm_count / ctas;
@@ -736,14 +958,32 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         cfg.attrs = attr;
         cfg.numAttrs = na;
         if (presplit) {
-            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, p));
-            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, p));
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
         } else {
-            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, false>, tmA, tmB, tmAlo, tmBlo, p));
-            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false>, tmA, tmB, tmAlo, tmBlo, p));
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, false>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false>, tmA, tmB, tmAlo, tmBlo, tmC, p));
         }
     }
     WK_CHECK_LAUNCH();
+    if (trace_env) {  // debugging aid: per-CTA milestones in ns relative to the earliest kernel entry
+        static unsigned long long host[512 * 16];
+        WK_CUDA(cudaStreamSynchronize(q->stream));
+        WK_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+        const unsigned n_cta = units * ctas < 512 ? units * ctas : 512;
+        unsigned long long t0 = ~0ull, t_end = 0;
+        for (unsigned c = 0; c < n_cta; c++) {
+            if (host[c * 16] && host[c * 16] < t0) t0 = host[c * 16];
+            if (host[c * 16 + 8] > t_end) t_end = host[c * 16 + 8];
+        }
+        fprintf(stderr, "[wk trace] %llux%llux%llu ctas=%d units=%u splits=%u: kernel span %.2f us; per CTA (us since first entry): entry setup tma0 raw0 mma0 mmaL accF epiD exit ld0|parked st0|synced st3|fold1 | chunk1: begin sts fence tma\n",
+                (unsigned long long)M, (unsigned long long)N, (unsigned long long)K, ctas, units, p.splits, (t_end - t0) * 1e-3);
+        for (unsigned c = 0; c < n_cta; c += (n_cta > 8 ? n_cta / 4 : 1)) {
+            fprintf(stderr, "[wk trace]  cta %3u:", c);
+            for (int s2 = 0; s2 <= 15; s2++) fprintf(stderr, " %6.2f", host[c * 16 + s2] ? (host[c * 16 + s2] - t0) * 1e-3 : -1.0);
+            fprintf(stderr, "\n");
+        }
+    }
     return WK_OK;
 }
 

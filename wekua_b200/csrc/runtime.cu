@@ -108,6 +108,9 @@ static void queue_fini(wk_queue *q) {
     for (void *r : q->retired) cudaFree(r);
     q->retired.clear();
     if (q->splitk_ws) cudaFree(q->splitk_ws);
+    if (q->align_ws) cudaFree(q->align_ws);
+    q->align_ws = nullptr;
+    q->align_ws_bytes = 0;
     if (q->int_ws) cudaFree(q->int_ws);
     q->int_ws = nullptr;
     q->int_ws_bytes = 0;
