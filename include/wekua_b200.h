@@ -200,6 +200,18 @@ int32_t wk_mse(wk_queue *q, int32_t dtype, const void *output, const void *expec
 /* fused backward prologue (linear.zig:608-613): sens *= act'(output) in one pass (sigmoid_dev o hadamard) */
 int32_t wk_act_backward(wk_queue *q, int32_t dtype, int32_t activation, const void *output, void *derivative_or_null,
                         void *sensitivity, uint64_t n);
+/* Linear.backward of one sub-layer, src/nn/layer/linear.zig:579-678, as ONE call: with s = sensitivity o act'(output),
+ * gradient[n_out,n_in] = s^T . prev_output, bias_gradient[n_out] = column sums of s (getBiasSensitivity :534-577),
+ * next_sensitivity[batch,n_in] = s . weight (skipped when NULL, :648).  f32 layers the tensor-core kernel can address run as
+ * THREE launches by default (one pass forms s in place and sums its columns, then the two GEMMs), TWO in mode 2 (s formed
+ * inside both GEMMs' converter stage; measured slower); everything else takes the reference's op-by-op
+ * sequence.  `sensitivity` is consumed (holds s or its old contents on return).  Pitches in elements. */
+int32_t wk_linear_backward(wk_queue *q, int32_t dtype, int32_t activation, uint64_t batch, uint64_t n_out, uint64_t n_in,
+                           void *sensitivity, uint64_t ld_s, const void *output, uint64_t ld_o, const void *prev_output,
+                           uint64_t ld_p, const void *weight, uint64_t ld_w, void *gradient, uint64_t ld_g,
+                           void *bias_gradient_or_null, void *next_sensitivity_or_null, uint64_t ld_n);
+/* test / tuning hook: 0 op-by-op, 1 fused element-wise pass + 2 GEMMs (default), 2 converter-stage prologue, -1 default */
+int32_t wk_linear_backward_set_mode(int32_t mode);
 /* optimizers: gdm.cl:3-33, adagrad.cl:3-48, rmsprop.cl:3-57 (FLT_EPSILON for both f32 and f64) */
 int32_t wk_gdm(wk_queue *q, int32_t dtype, void *x, const void *grad, void *velocity, const void *lr, const void *beta,
                uint64_t n);

@@ -123,6 +123,8 @@ SIGNATURES = {
     "wk_bias_step": [_vp, _i32, _vp, _vp, _u64, _u64, _u64],
     "wk_mse": [_vp, _i32, _vp, _vp, _vp, _vp, _u64],
     "wk_act_backward": [_vp, _i32, _i32, _vp, _vp, _vp, _u64],
+    "wk_linear_backward_set_mode": [_i32],
+    "wk_linear_backward": [_vp, _i32, _i32, _u64, _u64, _u64, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _u64],
     "wk_gdm": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _u64],
     "wk_adagrad": [_vp, _i32, _vp, _vp, _vp, _vp, _u64],
     "wk_rmsprop": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _u64],

@@ -404,9 +404,19 @@ template <typename BT, bool RANGE> struct UniformF<Cx<BT>, RANGE> {
 // through L1 at the point of use.  VECTOR = false is the same loop over single elements (row pitch or n not a
 // multiple of the vector width).  rp_units < 2^32 (host-checked).
 constexpr int kBiasUnroll = 8;
-template <typename T, bool VECTOR>
+template <typename T> __device__ __forceinline__ T bias_act_apply(T v, int) { return v; }
+template <> __device__ __forceinline__ float bias_act_apply<float>(float v, int act) {
+    return act == WK_ACT_SIGMOID ? wk_sigmoid(v) : act == WK_ACT_TANH ? wk_tanh(v) : v;
+}
+template <> __device__ __forceinline__ double bias_act_apply<double>(double v, int act) {
+    return act == WK_ACT_SIGMOID ? wk_sigmoid(v) : act == WK_ACT_TANH ? wk_tanh(v) : v;
+}
+
+// ACT: out = act(out + bias) in the same pass (Linear.forward's addBias + Activation.run, linear.zig:499-521, for layers whose
+// GEMM epilogue is not hidden behind another tile: see wk_gemm_bias_act)
+template <typename T, bool VECTOR, bool ACT = false>
 __global__ void __launch_bounds__(kThreads, 4) bias_add_kernel(T *__restrict__ out, const T *__restrict__ bias, uint32_t rp_units,
-                                                               uint64_t n_units) {
+                                                               uint64_t n_units, int act = 0) {
     constexpr int VEC = VECTOR ? 16 / (int)sizeof(T) : 1;
     union Pack { uint4 u; T e[16 / sizeof(T)]; };
     const uint64_t chunk = (uint64_t)kThreads * kBiasUnroll;
@@ -433,7 +443,10 @@ __global__ void __launch_bounds__(kThreads, 4) bias_add_kernel(T *__restrict__ o
                 if (VECTOR) b.u = __ldg(reinterpret_cast<const uint4 *>(bias) + col);
                 else b.e[0] = __ldg(bias + col);
 #pragma unroll
-                for (int e = 0; e < VEC; e++) o[u].e[e] += b.e[e];
+                for (int e = 0; e < VEC; e++) {
+                    o[u].e[e] += b.e[e];
+                    if (ACT) o[u].e[e] = bias_act_apply<T>(o[u].e[e], act);
+                }
                 if (VECTOR) st_na(reinterpret_cast<uint4 *>(out) + vi, o[u].u);
                 else out[vi] = o[u].e[0];
             }
@@ -815,6 +828,30 @@ WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void 
         return WK_OK;
     });
 }
+
+namespace wk {
+// out = act(out + bias[col]) over n contiguous elements of rows `row_pitch` long (f32 / f64; act != NONE)
+int32_t bias_act(wk_queue *q, int32_t dtype, void *output, const void *bias, uint64_t row_pitch, uint64_t n, int32_t act) {
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        constexpr uint64_t VEC = 16 / sizeof(scalar_t);
+        const bool vec = aligned16(output) && aligned16(bias) && row_pitch % VEC == 0 && n % VEC == 0;
+        const uint64_t n_units = vec ? n / VEC : n, rp_units = vec ? row_pitch / VEC : row_pitch;
+        if (n_units == 0) return WK_OK;
+        if (rp_units >= (1ull << 31)) return WK_ERR_INVALID_VALUE;
+        uint64_t blocks = (n_units + (uint64_t)kThreads * kBiasUnroll - 1) / ((uint64_t)kThreads * kBiasUnroll);
+        const uint64_t cap = (uint64_t)q->sm_count * 4;
+        if (blocks > cap) blocks = cap;
+        if (vec)
+            bias_add_kernel<scalar_t, true, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
+                                                                                               (uint32_t)rp_units, n_units, act);
+        else
+            bias_add_kernel<scalar_t, false, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
+                                                                                                (uint32_t)rp_units, n_units, act);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    });
+}
+}  // namespace wk
 
 WK_API int32_t wk_mse(wk_queue *q, int32_t dtype, const void *output, const void *expected, void *err, void *dev, uint64_t n) {
     WK_CHECK_QUEUE(q);

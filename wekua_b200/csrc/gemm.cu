@@ -14,6 +14,12 @@
 namespace wk {
 static int g_gemm_path = 0;  // 0 auto, 1 SIMT, 2 tensor-core (fail if not eligible)
 
+static int g_linear_backward_mode = -1;  // -1: environment / default
+static int linear_backward_mode() {
+    static const int env = [] { const char *e = getenv("WK_LINEAR_BACKWARD_FUSED"); return e && *e ? atoi(e) : 1; }();
+    return g_linear_backward_mode >= 0 ? g_linear_backward_mode : env;
+}
+
 static int gemm_path() {
     static int env = -1;
     if (env < 0) {
@@ -209,7 +215,97 @@ WK_API int32_t wk_gemm_bias_act(wk_queue *q, int32_t dtype, int32_t op_a, int32_
         return WK_ERR_TYPE_NOT_SUPPORTED;
     }
     if (act < WK_ACT_NONE || act > WK_ACT_TANH) return WK_ERR_INVALID_VALUE;
+    // f32: the tensor-core kernel's epilogue runs on four warps per SM.  With several tiles per SM it hides behind the next tile's
+    // MMAs and bias + activation ride along for free; with at most ~one tile per CTA pair it is exposed, and 256 expf / tanhf
+    // per thread cost more (measured: 20 us at 256 x 4096) than one more streaming pass over a dense C that still sits in L2.
+    const uint64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    if (dtype == 8 && (bias || act != WK_ACT_NONE) && ldc == N && tiles <= 2 * 74 && gemm_path() != 1) {
+        int32_t rc = gemm_any(q, dtype, op_a, op_b, M, N, K, nullptr, A, lda, B, ldb, nullptr, C, ldc, nullptr, WK_ACT_NONE, nullptr);
+        if (rc != WK_OK) return rc;
+        if (bias && act != WK_ACT_NONE) return bias_act(q, dtype, C, bias, ldc, M * ldc, act);
+        if (bias) return wk_bias_add(q, dtype, C, bias, ldc, M * ldc);
+        return wk_unary(q, dtype, act == WK_ACT_SIGMOID ? WK_OP_SIGMOID : WK_OP_TANH, C, M * ldc);
+    }
     return gemm_any(q, dtype, op_a, op_b, M, N, K, nullptr, A, lda, B, ldb, nullptr, C, ldc, bias, act, nullptr);
+}
+
+// Linear.backward of one (sub-)layer, src/nn/layer/linear.zig:579-678:
+//   d      = act'(output)                 (sigmoid.cl:22-38 / tanh.cl:3-20: from the layer OUTPUT)
+//   s      = sensitivity * d              (math.dot)
+//   grad   = s^T . prev_output            (gemm TN)          [n_out, n_in]
+//   bgrad  = column sums of s             (bias_step.cl)     [n_out]
+//   next   = s . weight                   (gemm NN)          [batch, n_in]      (skipped when next == NULL, linear.zig:648)
+// The reference issues 5 launches and moves [batch, n_out] through memory three extra times.  Modes (wk_linear_backward_set_mode
+// / WK_LINEAR_BACKWARD_FUSED):
+//   1 (default)  THREE launches: one pass writes s over `sensitivity` and sums its columns (the bias gradient) -- act', the
+//                Hadamard product and bias_step fused; then the two GEMMs at full speed.
+//   2            TWO launches (f32, tensor-core path): both GEMMs read `sensitivity` and `output` and form s in the converter
+//                stage; the TN GEMM's converters also add up the columns of s.  Measured SLOWER than mode 1 at every size
+//                (B = N = 8192: 16.7 vs 13.3 ms per layer step): the converter warps are the co-bottleneck of the 3xTF32
+//                pipeline, so work added there stretches every k-block, and the variant has two stages and no split-K.  Kept
+//                for the record and for the parity test; see DESIGN.md.
+//   0            the reference's op-by-op sequence.
+// `sensitivity` is CONSUMED: on return it holds s (modes 0, 1) or its old contents (mode 2) -- the reference overwrites it
+// before it is read again (mse.cl / the next backward GEMM).
+WK_API int32_t wk_linear_backward(wk_queue *q, int32_t dtype, int32_t activation, uint64_t batch, uint64_t n_out, uint64_t n_in,
+                                  void *sensitivity, uint64_t ld_s, const void *output, uint64_t ld_o, const void *prev_output,
+                                  uint64_t ld_p, const void *weight, uint64_t ld_w, void *gradient, uint64_t ld_g,
+                                  void *bias_gradient_or_null, void *next_sensitivity_or_null, uint64_t ld_n) {
+    WK_CHECK_QUEUE(q);
+    if (dtype != 8 && dtype != 9) {
+        set_error("linear_backward: f32/f64 only");
+        return WK_ERR_TYPE_NOT_SUPPORTED;
+    }
+    if (!sensitivity || !output || !prev_output || !weight || !gradient) return WK_ERR_INVALID_BUFFER;
+    if (activation < WK_ACT_NONE || activation > WK_ACT_TANH || batch == 0 || n_out == 0 || n_in == 0) return WK_ERR_INVALID_VALUE;
+    if (ld_s < n_out || ld_o < n_out || ld_p < n_in || ld_w < n_in || ld_g < n_in || (next_sensitivity_or_null && ld_n < n_in))
+        return WK_ERR_INVALID_VALUE;
+    const int mode = linear_backward_mode();
+    const bool big = (double)batch * (double)n_out * (double)n_in >= (double)(1 << 21);  // tiny layers stay launch-bound either way
+    if (mode == 2 && dtype == 8 && activation != WK_ACT_NONE && big && gemm_path() != 1 && ld_s == ld_o) {
+        GemmProlog pg{(const float *)output, ld_o, activation, (float *)bias_gradient_or_null};
+        int32_t rc = gemm_f32_tc(q, 1, 0, n_out, n_in, batch, nullptr, (const float *)sensitivity, ld_s, (const float *)prev_output, ld_p,
+                                 nullptr, (float *)gradient, ld_g, nullptr, WK_ACT_NONE, nullptr, &pg);
+        if (rc != -1) {
+            if (rc != WK_OK || !next_sensitivity_or_null) return rc;
+            GemmProlog pn{(const float *)output, ld_o, activation, nullptr};
+            rc = gemm_f32_tc(q, 0, 0, batch, n_in, n_out, nullptr, (const float *)sensitivity, ld_s, (const float *)weight, ld_w, nullptr,
+                             (float *)next_sensitivity_or_null, ld_n, nullptr, WK_ACT_NONE, nullptr, &pn);
+            if (rc != -1) return rc;
+            // (cannot happen: the same operands were addressable a moment ago) -- finish op by op from here
+            rc = wk_act_backward(q, dtype, activation, output, nullptr, sensitivity, batch * ld_s);
+            if (rc != WK_OK) return rc;
+            return gemm_any(q, dtype, 0, 0, batch, n_in, n_out, nullptr, sensitivity, ld_s, weight, ld_w, nullptr, next_sensitivity_or_null,
+                            ld_n, nullptr, WK_ACT_NONE, nullptr);
+        }
+    }
+    int32_t rc = WK_OK;
+    bool bias_done = false;
+    if (activation != WK_ACT_NONE) {
+        if (mode >= 1 && bias_gradient_or_null) {  // ONE pass: s = sensitivity * act'(output) written back, its columns summed
+            rc = act_backward_colsum(q, dtype, activation, output, ld_o, sensitivity, ld_s, batch, n_out, bias_gradient_or_null);
+            bias_done = true;
+        } else {  // whole rows (pad columns included), like the reference's 1-D launches over the buffer
+            rc = wk_act_backward(q, dtype, activation, output, nullptr, sensitivity, batch * ld_s);
+        }
+        if (rc != WK_OK) return rc;
+    }
+    rc = gemm_any(q, dtype, 1, 0, n_out, n_in, batch, nullptr, sensitivity, ld_s, prev_output, ld_p, nullptr, gradient, ld_g, nullptr,
+                  WK_ACT_NONE, nullptr);
+    if (rc != WK_OK) return rc;
+    if (bias_gradient_or_null && !bias_done) {
+        rc = wk_bias_step(q, dtype, sensitivity, bias_gradient_or_null, ld_s, batch, n_out);
+        if (rc != WK_OK) return rc;
+    }
+    if (!next_sensitivity_or_null) return WK_OK;
+    return gemm_any(q, dtype, 0, 0, batch, n_in, n_out, nullptr, sensitivity, ld_s, weight, ld_w, nullptr, next_sensitivity_or_null, ld_n,
+                    nullptr, WK_ACT_NONE, nullptr);
+}
+
+WK_API int32_t wk_linear_backward_set_mode(int32_t mode) {
+    if (mode < -1 || mode > 2) return WK_ERR_INVALID_VALUE;
+    g_linear_backward_mode = mode;
+    return WK_OK;
 }
 
 WK_API int32_t wk_gemm_rowshard_allgather(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, uint64_t M_local, uint64_t N,

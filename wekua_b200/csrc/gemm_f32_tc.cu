@@ -38,14 +38,16 @@ constexpr int EPI_PITCH = 36;                                // floats per row o
 constexpr int EPI_WARP_BYTES = 8192;                         // per epilogue warp: two 32 x 32 fp32 TMA-store staging boxes (swizzled, 4 KiB each)
 constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;        // 32 KiB, 1024-byte aligned (right after the stages)
 
-template <int CTAS> struct Cfg {
+template <int CTAS, bool PROL = false> struct Cfg {
     static constexpr int BN_LOAD = BN / CTAS;          // B columns staged by each CTA
     static constexpr int A_BYTES = BM * BK * 4;        // 16 KiB
     static constexpr int B_BYTES = BN_LOAD * BK * 4;   // 32 / 16 KiB
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;  // hi tiles (TMA lands here)
-    static constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // + lo tiles
-    static constexpr int STAGES = CTAS == 1 ? 2 : 3;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int Y_BYTES = PROL ? A_BYTES : 0;   // PROL: the tile of Y that multiplies the A tile (same geometry)
+    static constexpr int STAGE_BYTES = 2 * RAW_BYTES + Y_BYTES;  // + lo tiles (+ Y tile)
+    static constexpr int STAGES = PROL ? 2 : (CTAS == 1 ? 2 : 3);
+    static constexpr int COLSUM_BYTES = PROL ? 4096 : 0;  // PROL: per-warp column-sum partials of the converter warps
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + COLSUM_BYTES + 1024 /*align slack*/;
 };
 
 struct Params {
@@ -71,6 +73,11 @@ struct Params {
     int n_peers, self;
     int peer_bulk;  // fused all-gather: peers receive whole 128-byte row segments as bulk async copies from the staging tile
     float *peers[16];
+    // A-prologue (Linear.backward, src/nn/layer/linear.zig:608-613 fused into the GEMM that consumes it): the A operand is
+    // used as A o act'(Y), Y = the layer output with A's shape and layout; colsum (op_a = T only) receives the column sums
+    // of A o act'(Y) over K -- getBiasSensitivity, linear.zig:534-577 -- from the tiles of the first tile column
+    int prol_act;
+    float *colsum;
     // WK_GEMM_TRACE=1 (debugging aid for launch-bound problems): %globaltimer stamps of the pipeline's milestones, 16 slots per CTA
     unsigned long long *trace;
 };
@@ -142,12 +149,13 @@ template <int CTAS> __device__ __forceinline__ void arrive_on_leader(uint64_t *b
 
 // PRE: the lo planes were computed by split_lo_kernel beforehand and arrive by TMA next to the raw tiles; the converter warps
 // only relay the barrier (no shared-memory traffic of their own).  Same arithmetic, bit-identical results (split mode 1).
-template <int CTAS, bool PRE>
+template <int CTAS, bool PRE, bool PROL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                    const __grid_constant__ CUtensorMap tmC, const Params p) {
-    using C = Cfg<CTAS>;
+    static_assert(!(PRE && PROL), "the pre-split experiment has no prologue variant");
+    using C = Cfg<CTAS, PROL>;  // PROL: tmAlo is the tensor map of Y
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RAW_BYTES = C::RAW_BYTES, A_BYTES = C::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic smem base has the same CTA-relative offset in both CTAs of a pair, so the aligned tiles do too
@@ -205,7 +213,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&bars->stage_free[s], ph ^ 1);
                     uint8_t *a_dst = smem + s * STAGE_BYTES, *b_dst = a_dst + A_BYTES;
-                    mbar_arrive_expect_tx(&bars->raw_full[s], PRE ? 2 * RAW_BYTES : RAW_BYTES);
+                    mbar_arrive_expect_tx(&bars->raw_full[s], PRE ? 2 * RAW_BYTES : RAW_BYTES + C::Y_BYTES);
+                    if (PROL) {  // the Y tile: A's boxes, landing behind the lo tiles
+                        uint8_t *yd = a_dst + 2 * RAW_BYTES;
+                        const int32_t ky = (int32_t)(kb * BK);
+                        if (p.op_a == 0) tma_load_2d(yd, &tmAlo, ky, m0, &bars->raw_full[s]);
+                        else
+                            for (int j = 0; j < BM / 32; j++) tma_load_2d(yd + j * 4096, &tmAlo, m0 + 32 * j, ky, &bars->raw_full[s]);
+                    }
                     const int32_t k0 = (int32_t)(kb * BK);
 #pragma unroll
                     for (int plane = 0; plane < (PRE ? 2 : 1); plane++) {  // raw tiles, then (PRE) the lo tiles RAW_BYTES further on
@@ -289,6 +304,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (uint32_t w = unit; w < num_tiles; w += n_units) {
             uint32_t t, sp, kb0, kb1;
             work_coords(p, w, num_kb, t, sp, kb0, kb1);
+            // PROL: column sums of A o act'(Y) over K (the bias gradient), taken by the tiles of the first tile column while
+            // the operand passes through the converters' registers anyway
+            bool do_colsum = false;
+            uint32_t cs_m0 = 0;
+            float4 cs[4];
+            if (PROL) {
+                uint32_t tm, tn;
+                tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
+                do_colsum = p.colsum != nullptr && tn == 0;
+                cs_m0 = (tm * CTAS + rank) * BM;
+#pragma unroll
+                for (int j = 0; j < 4; j++) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             for (uint32_t kb = kb0; kb < kb1; kb++, it++) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&bars->raw_full[s], ph);
@@ -300,11 +328,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
                 float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + RAW_BYTES);
+                const float4 *yt = reinterpret_cast<const float4 *>(smem + s * STAGE_BYTES + 2 * RAW_BYTES);
 #pragma unroll
                 for (int j = 0; j < RAW_BYTES / 16 / (CONV_WARPS * 32); j++) {
                     const int i = ct + j * (CONV_WARPS * 32);
                     const float4 x = hi[i];
-                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    float xs[4] = {x.x, x.y, x.z, x.w};
+                    const bool a_part = PROL && j < A_BYTES / 16 / (CONV_WARPS * 32);  // the first 4 pieces of a thread lie in A
+                    if (a_part) {
+                        // a' = a * act'(y), the arithmetic of wk_act_backward (ActBackwardF) without FMA contraction, so the
+                        // fused operand is bit-identical to the tensor the unfused sequence stores
+                        const float4 y4 = yt[i];
+                        const float ys[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float d = p.prol_act == WK_ACT_SIGMOID ? __fmul_rn(ys[e], __fsub_rn(1.0f, ys[e]))
+                                                                          : __fsub_rn(1.0f, __fmul_rn(ys[e], ys[e]));
+                            xs[e] = __fmul_rn(xs[e], d);
+                        }
+                        if (do_colsum) {
+                            cs[j].x += xs[0]; cs[j].y += xs[1]; cs[j].z += xs[2]; cs[j].w += xs[3];
+                        }
+                    }
                     float hs[4], ls[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
@@ -319,12 +364,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         ls[e] = __uint_as_float(lb);
                     }
                     if (split == 0) hi[i] = make_float4(hs[0], hs[1], hs[2], hs[3]);
+                    else if (a_part) hi[i] = make_float4(xs[0], xs[1], xs[2], xs[3]);  // the product replaces the raw tile
                     lo[i] = make_float4(ls[0], ls[1], ls[2], ls[3]);
                 }
                 // generic-proxy smem writes -> visible to the tensor core (async proxy), then release to the MMA warp
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) arrive_on_leader<CTAS>(&bars->conv_done[s]);
+            }
+            if (PROL && p.colsum != nullptr) {  // (uniform over the CTA's converter warps: named barrier 2)
+                // A is MN-major here (op_a = T): thread ct holds, in box j (32 m x 32 k), row k = ct >> 3 and the physical 16-byte
+                // piece ct & 7; the 32-byte-atom swizzle (Swizzle<2,5,2>) puts logical piece lc at lc ^ ((k & 3) << 1).  A warp
+                // covers 4 rows: two shuffles add them per logical piece, the 8 warps' results meet in shared memory and are
+                // added in warp order -- a fixed order, no atomics.
+                float4 *part = reinterpret_cast<float4 *>(smem + STAGES * STAGE_BYTES + EPI_BYTES + 256);
+                const int cw = ct >> 5, r_loc = (ct >> 3) & 3, lc = (ct & 7) ^ (r_loc << 1);
+                if (do_colsum) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float4 v = cs[j];
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, 10); v.y += __shfl_xor_sync(0xffffffffu, v.y, 10);
+                        v.z += __shfl_xor_sync(0xffffffffu, v.z, 10); v.w += __shfl_xor_sync(0xffffffffu, v.w, 10);
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, 20); v.y += __shfl_xor_sync(0xffffffffu, v.y, 20);
+                        v.z += __shfl_xor_sync(0xffffffffu, v.z, 20); v.w += __shfl_xor_sync(0xffffffffu, v.w, 20);
+                        if (r_loc == 0) part[(cw * 4 + j) * 8 + lc] = v;
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(CONV_WARPS * 32) : "memory");
+                if (do_colsum && ct < BM) {
+                    const int j = ct >> 5, l2 = (ct >> 2) & 7, e = ct & 3;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < CONV_WARPS; w8++) {
+                        const float4 v = part[(w8 * 4 + j) * 8 + l2];
+                        sum += e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w;
+                    }
+                    if (cs_m0 + ct < p.M) p.colsum[cs_m0 + ct] = sum;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(CONV_WARPS * 32) : "memory");
             }
         }
     } else {
@@ -756,8 +833,12 @@ static int env_int(const char *name, int dflt) {
 
 int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_t N, uint64_t K, const float *alpha,
                     const float *A, uint64_t lda, const float *B, uint64_t ldb, const float *beta, float *C, uint64_t ldc,
-                    const float *bias, int32_t act, const GemmPeers *peers) {
+                    const float *bias, int32_t act, const GemmPeers *peers, const GemmProlog *prolog) {
     using namespace tc;
+    if (prolog) {
+        if (!aligned16(prolog->Y) || (prolog->ldy % 4) || (prolog->colsum && op_a != 1) || (peers && peers->n > 1)) return -1;
+        if (prolog->act != WK_ACT_SIGMOID && prolog->act != WK_ACT_TANH) return -1;
+    }
     // TMA needs 16-byte aligned bases and pitches; the epilogue wants 16-byte aligned C rows
     // (gemm.cu stages unaligned A / B into an aligned scratch first; an unaligned C takes the epilogue's element-wise stores)
     if (!aligned16(A) || !aligned16(B) || (lda % 4) || (ldb % 4)) return -1;
@@ -771,7 +852,8 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     // CTA pairs (256 x 256 tiles) when the problem has at least two row tiles per pair to share; WK_GEMM_CTAS overrides
     static const int ctas_env = env_int("WK_GEMM_CTAS", 0);
     static const int split_env = env_int("WK_GEMM_SPLIT", 1);
-    const int ctas = ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1);
+    // (the prologue variant exists for CTA pairs only: a single CTA's 128 x 256 stage plus the Y tile leaves room for one stage)
+    const int ctas = prolog ? 2 : (ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1));
     const uint32_t bn_load = BN / ctas;
 
     CUtensorMap tmA, tmB;
@@ -787,7 +869,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     // WK_GEMM_PRESPLIT=1 (experimental, off by default): lo planes computed in one streaming pass per operand and loaded by
     // TMA, so the converter warps move no shared memory.  Costs an operand-sized workspace and 2x the L2 -> SM traffic.
     static const int presplit_env = env_int("WK_GEMM_PRESPLIT", 0);
-    const bool presplit = presplit_env && split_env == 1;
+    const bool presplit = presplit_env && split_env == 1 && !prolog;
     CUtensorMap tmAlo = tmA, tmBlo = tmB;
     if (presplit) {
         const uint64_t a_rows = op_a ? K : M, a_cols = op_a ? M : K, b_rows = op_b ? N : K, b_cols = op_b ? K : N;
@@ -812,7 +894,17 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         }
     }
 
+    if (prolog) {  // Y travels in the tmAlo slot: A's geometry over Y's memory
+        if (op_a == 0) ok = make_tmap_2d(&tmAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, prolog->Y, K, M, prolog->ldy * 4, BK, BM);
+        else ok = make_tmap_2d(&tmAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, prolog->Y, M, K, prolog->ldy * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!ok) {
+            set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed (prologue operand)");
+            return WK_ERR_CUDA;
+        }
+    }
     Params p{};
+    p.prol_act = prolog ? prolog->act : 0;
+    p.colsum = prolog ? prolog->colsum : nullptr;
     p.C = C;
     p.M = M; p.N = N; p.K = K; p.ldc = ldc;
     p.c_vec = aligned16(C) && ldc % 4 == 0;
@@ -844,6 +936,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
         WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
         WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+        WK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2, true>::SMEM_BYTES));
         attr_set[q->device & 63] = true;
     }
     static int max_pairs[64] = {0};  // co-resident CTA pairs (GPCs with an odd SM count strand one SM), per device
@@ -873,9 +966,10 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     static const int debug_env = env_int("WK_DEBUG", 0);
     uint32_t splits = 1;
     uint64_t n_full = 0;  // unsplit tiles
-    if (splitk_env > 0) splits = (uint32_t)splitk_env;
+    if (prolog) splits = 1;  // (the prologue variant keeps one k-range per tile: its column sums cover all of K)
+    else if (splitk_env > 0) splits = (uint32_t)splitk_env;
     else if (n_out_tiles * 2 <= units_avail) splits = (uint32_t)(units_avail / n_out_tiles);
-    else if (tail_env && num_kb >= 16) {
+    else if (tail_env && num_kb >= 16 && !prolog) {
         // wave quantisation: the persistent schedule runs ceil(tiles / units) rounds; when the last round is at most half
         // full (N = 4096: 256 tiles = 3 rounds of 74 + 34), its tiles are split along K so the round costs 1/splits
         const uint64_t rem = n_out_tiles % units_avail;
@@ -935,7 +1029,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(units * ctas);
         cfg.blockDim = dim3(THREADS);
-        cfg.dynamicSmemBytes = ctas == 1 ? Cfg<1>::SMEM_BYTES : Cfg<2>::SMEM_BYTES;
+        cfg.dynamicSmemBytes = prolog ? Cfg<2, true>::SMEM_BYTES : (ctas == 1 ? Cfg<1>::SMEM_BYTES : Cfg<2>::SMEM_BYTES);
         cfg.stream = q->stream;
         cudaLaunchAttribute attr[2];
         int na = 0;
@@ -957,7 +1051,9 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        if (presplit) {
+        if (prolog) {
+            WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+        } else if (presplit) {
             if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
             else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
         } else {

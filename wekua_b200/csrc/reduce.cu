@@ -191,9 +191,13 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
 // is exactly the reference's.
 // VECTOR: a thread owns one 128-bit group of columns (row pitch a multiple of the vector width, aligned rows) and keeps
 // 8 row vectors in flight; per column the additions are the same ones in the same order.
-template <typename T, bool VECTOR>
+// ACT != 0 (fused first step of Linear.backward, linear.zig:608-613 + :534-577 in ONE pass): the summed value is
+// s * act'(y) -- the arithmetic of ActBackwardF, no FMA contraction in this translation unit -- and it is also written back
+// over s, so the two GEMMs that follow read the finished sensitivity.
+template <typename T, bool VECTOR, int ACT = 0>
 __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, uint64_t rp, uint64_t rows, uint64_t n_cols,
-                                                     uint64_t rows_per, T *__restrict__ out, uint64_t out_pitch) {
+                                                     uint64_t rows_per, T *__restrict__ out, uint64_t out_pitch,
+                                                     const T *__restrict__ y = nullptr, uint64_t y_rp = 0, T *s_out = nullptr) {
     constexpr int VEC = VECTOR ? 16 / (int)sizeof(T) : 1;
     union Pack { uint4 u; T e[16 / sizeof(T)]; };
     const uint64_t c = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * VEC;
@@ -207,22 +211,40 @@ __global__ void __launch_bounds__(256) colsum_stage1(const T *__restrict__ s, ui
     const T *p = s + r0 * rp + c;
     auto load = [](const T *q) {
         Pack v;
-        if (VECTOR) v.u = __ldg(reinterpret_cast<const uint4 *>(q));
+        if (VECTOR) v.u = ACT ? *reinterpret_cast<const uint4 *>(q) : __ldg(reinterpret_cast<const uint4 *>(q));  // (ACT: s is rewritten)
         else v.e[0] = *q;
         return v;
     };
+    auto finish = [&](Pack &a, uint64_t row) {  // ACT: a = s * act'(y), stored back
+        if (ACT) {
+            const Pack yv = load(y + row * y_rp + c);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const T yy = yv.e[e];
+                const T d = ACT == WK_ACT_SIGMOID ? yy * ((T)1 - yy) : (T)1 - yy * yy;
+                a.e[e] = a.e[e] * d;
+            }
+            T *o = s_out + row * rp + c;
+            if (VECTOR) *reinterpret_cast<uint4 *>(o) = a.u;
+            else *o = a.e[0];
+        }
+    };
     uint64_t r = r0;
-    for (; r + 8 <= r1; r += 8, p += 8 * rp) {  // 8 row vectors in flight, summed in row order
-        Pack a[8];
+    constexpr int FLY = ACT ? 4 : 8;  // row vectors in flight (ACT carries the y vectors as well), summed in row order
+    for (; r + FLY <= r1; r += FLY, p += FLY * rp) {
+        Pack a[FLY];
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = load(p + i * rp);
+        for (int i = 0; i < FLY; i++) a[i] = load(p + i * rp);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < FLY; i++) finish(a[i], r + i);
+#pragma unroll
+        for (int i = 0; i < FLY; i++)
 #pragma unroll
             for (int e = 0; e < VEC; e++) acc[e] += a[i].e[e];
     }
     for (; r < r1; r++, p += rp) {
-        const Pack a = load(p);
+        Pack a = load(p);
+        finish(a, r);
 #pragma unroll
         for (int e = 0; e < VEC; e++) acc[e] += a.e[e];
     }
@@ -303,53 +325,76 @@ WK_API int32_t wk_dot_reduce_async(wk_queue *q, int32_t dtype, uint64_t depth, u
     });
 }
 
+namespace wk {
+// column sums of sens (optionally of sens * act'(y), written back over sens): the launcher behind wk_bias_step and the fused
+// first step of wk_linear_backward
+template <typename scalar_t, int ACT>
+static int32_t colsum_launch(wk_queue *q, scalar_t *sens, scalar_t *bias_grad, uint64_t row_pitch, uint64_t rows, uint64_t n_cols,
+                             const scalar_t *y, uint64_t y_rp) {
+    constexpr uint64_t VEC = 16 / sizeof(scalar_t);
+    // the vector kernel reads whole 128-bit column groups: the last group may reach into the row's padding columns
+    const bool vec = aligned16(sens) && row_pitch % VEC == 0 && (n_cols + VEC - 1) / VEC * VEC <= row_pitch &&
+                     (!ACT || (aligned16(y) && y_rp % VEC == 0 && (n_cols + VEC - 1) / VEC * VEC <= y_rp));
+    const uint64_t col_units = vec ? (n_cols + VEC - 1) / VEC : n_cols;
+    const uint64_t gx = (col_units + 255) / 256;
+    // enough chunks to fill the machine, but never split short columns (keeps the reference's order)
+    uint64_t chunks = 1;
+    if (rows > 256 || (ACT && rows >= 32)) {  // (the fused pass is a new op: no reference summation order to keep for short columns)
+        // exactly one resident wave: (blocks that fit on an SM) x SMs, so no partial second wave trails behind
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec ? colsum_stage1<scalar_t, true, ACT> : colsum_stage1<scalar_t, false, ACT>,
+                                                          256, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+        chunks = ((uint64_t)q->sm_count * per_sm) / gx;
+        const uint64_t max_chunks = ACT ? (rows + 7) / 8 : (rows + 63) / 64;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks > 65535) chunks = 65535;
+        if (chunks < 1) chunks = 1;
+    }
+    const uint64_t rows_per = (rows + chunks - 1) / chunks;
+    auto stage1 = [&](scalar_t *out, uint64_t out_pitch) {
+        const dim3 grid((unsigned)gx, (unsigned)chunks);
+        if (vec)
+            colsum_stage1<scalar_t, true, ACT><<<grid, 256, 0, q->stream>>>(sens, row_pitch, rows, n_cols, rows_per, out, out_pitch, y, y_rp, sens);
+        else
+            colsum_stage1<scalar_t, false, ACT><<<grid, 256, 0, q->stream>>>(sens, row_pitch, rows, n_cols, rows_per, out, out_pitch, y, y_rp, sens);
+    };
+    if (chunks == 1) {
+        stage1(bias_grad, 0);
+        WK_CHECK_LAUNCH();
+        return WK_OK;
+    }
+    int32_t rc = ensure_scratch(q, chunks * n_cols * sizeof(scalar_t));
+    if (rc != WK_OK) return rc;
+    stage1((scalar_t *)q->scratch, n_cols);
+    WK_CHECK_LAUNCH();
+    colsum_stage2<scalar_t><<<(unsigned)((n_cols + 31) / 32), dim3(32, 8), 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
+                                                                                         bias_grad);
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
+
+// sens *= act'(output) and bias_grad = column sums of the result, one pass over [rows, n_cols] (f32 / f64)
+int32_t act_backward_colsum(wk_queue *q, int32_t dtype, int32_t act, const void *output, uint64_t out_pitch, void *sens,
+                            uint64_t row_pitch, uint64_t rows, uint64_t n_cols, void *bias_grad) {
+    return WK_DISPATCH_FLOAT(dtype, [&]() -> int32_t {
+        if (act == WK_ACT_SIGMOID)
+            return colsum_launch<scalar_t, WK_ACT_SIGMOID>(q, (scalar_t *)sens, (scalar_t *)bias_grad, row_pitch, rows, n_cols,
+                                                           (const scalar_t *)output, out_pitch);
+        return colsum_launch<scalar_t, WK_ACT_TANH>(q, (scalar_t *)sens, (scalar_t *)bias_grad, row_pitch, rows, n_cols,
+                                                    (const scalar_t *)output, out_pitch);
+    });
+}
+}  // namespace wk
+
 WK_API int32_t wk_bias_step(wk_queue *q, int32_t dtype, const void *sens, void *bias_grad, uint64_t row_pitch, uint64_t rows,
                             uint64_t n_cols) {
     WK_CHECK_QUEUE(q);
     if (!sens || !bias_grad) return WK_ERR_INVALID_BUFFER;
     if (n_cols == 0) return WK_ERR_INVALID_VALUE;
     return WK_DISPATCH_REAL(dtype, [&]() -> int32_t {
-        constexpr uint64_t VEC = 16 / sizeof(scalar_t);
-        // the vector kernel reads whole 128-bit column groups: the last group may reach into the row's padding columns
-        const bool vec = aligned16(sens) && row_pitch % VEC == 0 && (n_cols + VEC - 1) / VEC * VEC <= row_pitch;
-        const uint64_t col_units = vec ? (n_cols + VEC - 1) / VEC : n_cols;
-        const uint64_t gx = (col_units + 255) / 256;
-        // enough chunks to fill the machine, but never split short columns (keeps the reference's order)
-        uint64_t chunks = 1;
-        if (rows > 256) {
-            // exactly one resident wave: (blocks that fit on an SM) x SMs, so no partial second wave trails behind
-            int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec ? colsum_stage1<scalar_t, true> : colsum_stage1<scalar_t, false>,
-                                                              256, 0) != cudaSuccess || per_sm < 1) {
-                cudaGetLastError();
-                per_sm = 4;
-            }
-            chunks = ((uint64_t)q->sm_count * per_sm) / gx;
-            const uint64_t max_chunks = (rows + 63) / 64;
-            if (chunks > max_chunks) chunks = max_chunks;
-            if (chunks > 65535) chunks = 65535;
-            if (chunks < 1) chunks = 1;
-        }
-        const uint64_t rows_per = (rows + chunks - 1) / chunks;
-        auto stage1 = [&](scalar_t *out, uint64_t out_pitch) {
-            const dim3 grid((unsigned)gx, (unsigned)chunks);
-            if (vec)
-                colsum_stage1<scalar_t, true><<<grid, 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, out, out_pitch);
-            else
-                colsum_stage1<scalar_t, false><<<grid, 256, 0, q->stream>>>((const scalar_t *)sens, row_pitch, rows, n_cols, rows_per, out, out_pitch);
-        };
-        if (chunks == 1) {
-            stage1((scalar_t *)bias_grad, 0);
-            WK_CHECK_LAUNCH();
-            return WK_OK;
-        }
-        int32_t rc = ensure_scratch(q, chunks * n_cols * sizeof(scalar_t));
-        if (rc != WK_OK) return rc;
-        stage1((scalar_t *)q->scratch, n_cols);
-        WK_CHECK_LAUNCH();
-        colsum_stage2<scalar_t><<<(unsigned)((n_cols + 31) / 32), dim3(32, 8), 0, q->stream>>>((const scalar_t *)q->scratch, chunks, n_cols, n_cols,
-                                                                    (scalar_t *)bias_grad);
-        WK_CHECK_LAUNCH();
-        return WK_OK;
+        return wk::colsum_launch<scalar_t, 0>(q, (scalar_t *)const_cast<void *>(sens), (scalar_t *)bias_grad, row_pitch, rows, n_cols, nullptr, 0);
     });
 }

@@ -177,29 +177,39 @@ class Linear:
         output = cache.outputs[index]
         while True:
             acti_derivative = cache.acti_derivatives[index]
-            if self.fused and self.activation is not None:
-                capi.check(capi.lib().wk_act_backward(pipeline.q, sens.type_index, self.activation.kind, output.ptr,
-                                                      acti_derivative.ptr, sens.ptr, sens.flat_elements("activation backward")))
+            prev_output = cache.outputs[index - 1] if index >= 1 else input_tensor
+            if index >= 1:
+                next_sens = cache.sensitivities[index - 1]
+            else:
+                next_sens = input_sensitivity
+            if self.fused:
+                # one call: act' o sensitivity formed inside the two GEMMs (f32, tensor-core path: 2 launches), the bias
+                # gradient summed inside the first; otherwise the library runs the op-by-op sequence itself
+                grad = cache.gradients[index]
+                bgrad = cache.bias_gradients[index] if self.bias_enabled else None
+                capi.check(capi.lib().wk_linear_backward(
+                    pipeline.q, sens.type_index, self.activation.kind if self.activation is not None else ACT_NONE,
+                    sens.shape[0], sens.shape[1], self.weights[index].shape[1], sens.ptr, sens.row_pitch, output.ptr,
+                    output.row_pitch, prev_output.ptr, prev_output.row_pitch, self.weights[index].ptr,
+                    self.weights[index].row_pitch, grad.ptr, grad.row_pitch, bgrad.ptr if bgrad is not None else None,
+                    next_sens.ptr if next_sens is not None else None, next_sens.row_pitch if next_sens is not None else 0))
+                blas.finish_c_padding(pipeline, grad, None)
+                if next_sens is not None:
+                    blas.finish_c_padding(pipeline, next_sens, None)
             else:
                 if self.activation is not None:
                     self.activation.get_derivative(pipeline, output, acti_derivative)
                 wmath.dot(pipeline, sens, acti_derivative)
-            prev_output = cache.outputs[index - 1] if index >= 1 else input_tensor
-            output = prev_output
-            blas.gemm(pipeline, None, sens, blas.Operation.transpose, prev_output, blas.Operation.no_transpose, None,
-                      cache.gradients[index], cache.grad_packed[index])
-            if self.bias_enabled:
-                self._bias_sensitivity(pipeline, sens, cache.bias_gradients[index])
-            if index >= 1:
-                next_sens = cache.sensitivities[index - 1]
-            else:
-                if input_sensitivity is None:
-                    return
-                next_sens = input_sensitivity
-            blas.gemm(pipeline, None, sens, blas.Operation.no_transpose, self.weights[index], blas.Operation.no_transpose,
-                      None, next_sens, cache.sensitivity_packed[index])
-            if index == 0:
+                blas.gemm(pipeline, None, sens, blas.Operation.transpose, prev_output, blas.Operation.no_transpose, None,
+                          cache.gradients[index], cache.grad_packed[index])
+                if self.bias_enabled:
+                    self._bias_sensitivity(pipeline, sens, cache.bias_gradients[index])
+                if next_sens is not None:
+                    blas.gemm(pipeline, None, sens, blas.Operation.no_transpose, self.weights[index], blas.Operation.no_transpose,
+                              None, next_sens, cache.sensitivity_packed[index])
+            if next_sens is None or index == 0:
                 break
+            output = prev_output
             index -= 1
             sens = next_sens
 

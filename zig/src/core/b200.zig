@@ -132,6 +132,8 @@ pub extern fn wk_bias_add(q: *Queue, dtype: i32, output: ?*anyopaque, bias: ?*co
 pub extern fn wk_bias_step(q: *Queue, dtype: i32, sensitivity: ?*const anyopaque, bias_grad: ?*anyopaque, row_pitch: u64, rows: u64, n_cols: u64) i32;
 pub extern fn wk_mse(q: *Queue, dtype: i32, output: ?*const anyopaque, expected: ?*const anyopaque, error_tensor: ?*anyopaque, dev_or_null: ?*anyopaque, n: u64) i32;
 pub extern fn wk_act_backward(q: *Queue, dtype: i32, activation: i32, output: ?*const anyopaque, derivative_or_null: ?*anyopaque, sensitivity: ?*anyopaque, n: u64) i32;
+pub extern fn wk_linear_backward(q: *Queue, dtype: i32, activation: i32, batch: u64, n_out: u64, n_in: u64, sensitivity: ?*anyopaque, ld_s: u64, output: ?*const anyopaque, ld_o: u64, prev_output: ?*const anyopaque, ld_p: u64, weight: ?*const anyopaque, ld_w: u64, gradient: ?*anyopaque, ld_g: u64, bias_gradient_or_null: ?*anyopaque, next_sensitivity_or_null: ?*anyopaque, ld_n: u64) i32;
+pub extern fn wk_linear_backward_set_mode(mode: i32) i32;
 pub extern fn wk_gdm(q: *Queue, dtype: i32, x: ?*anyopaque, grad: ?*const anyopaque, velocity: ?*anyopaque, lr: ?*const anyopaque, beta: ?*const anyopaque, n: u64) i32;
 pub extern fn wk_adagrad(q: *Queue, dtype: i32, x: ?*anyopaque, grad: ?*const anyopaque, history: ?*anyopaque, lr: ?*const anyopaque, n: u64) i32;
 pub extern fn wk_rmsprop(q: *Queue, dtype: i32, x: ?*anyopaque, grad: ?*const anyopaque, history: ?*anyopaque, lr: ?*const anyopaque, gamma: ?*const anyopaque, n: u64) i32;

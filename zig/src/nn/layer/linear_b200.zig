@@ -39,3 +39,12 @@ pub fn forwardFused(comptime T: type, pipeline: *Pipeline, input: *Tensor(T), we
 pub fn backwardActivation(comptime T: type, pipeline: *Pipeline, activation_kind: i32, output: *Tensor(T), derivative: ?*Tensor(T), sensitivity: *Tensor(T)) TensorErrors!void {
     try b200.check(b200.wk_act_backward(pipeline.q(), core.types.getTypeIndex(T), activation_kind, output.buffer, if (derivative) |d| d.buffer else null, sensitivity.buffer, sensitivity.dimensions.number_of_elements));
 }
+
+/// the whole backward step of one sub-layer (linear.zig:579-678: getDerivative, math.dot, gemm TN, getBiasSensitivity, gemm NN)
+/// as ONE call -- two launches for f32 layers on the tensor-core path; `sensitivity` is consumed
+pub fn backwardFused(comptime T: type, pipeline: *Pipeline, activation_kind: i32, sensitivity: *Tensor(T), output: *Tensor(T), prev_output: *Tensor(T), weight: *Tensor(T), gradient: *Tensor(T), bias_gradient: ?*Tensor(T), next_sensitivity: ?*Tensor(T)) TensorErrors!void {
+    const batch = sensitivity.dimensions.shape[0];
+    const n_out = sensitivity.dimensions.shape[1];
+    const n_in = weight.dimensions.shape[1];
+    try b200.check(b200.wk_linear_backward(pipeline.q(), core.types.getTypeIndex(T), activation_kind, batch, n_out, n_in, sensitivity.buffer, sensitivity.memory_layout.row_pitch, output.buffer, output.memory_layout.row_pitch, prev_output.buffer, prev_output.memory_layout.row_pitch, weight.buffer, weight.memory_layout.row_pitch, gradient.buffer, gradient.memory_layout.row_pitch, if (bias_gradient) |b| b.buffer else null, if (next_sensitivity) |n| n.buffer else null, if (next_sensitivity) |n| n.memory_layout.row_pitch else 0));
+}
