@@ -489,6 +489,20 @@ def freivalds_gather_check(wk, ctx, pipe, a_blk, b, c_full, N, rows, row0, rank,
             "max_err": max(o_[1] for o_ in oks), "bound": min(o_[2] for o_ in oks)}
 
 
+def host_link_ceiling(g, h2d_bytes, d2h_bytes):
+    """the measured host<->device copy ceiling of this box class (tools/pcie_peak.py -> profiles/pcie_peak_r02_g{g}.json): time
+    the step's copies alone would take, one direction after the other at the all-ranks rates, and both at once"""
+    path = os.path.join(ROOT, "profiles", f"pcie_peak_r02_g{g}.json")
+    if not os.path.exists(path):
+        return None
+    d = json.loads(open(path).read().strip().splitlines()[-1])
+    serial_ms = (h2d_bytes / (d["h2d"]["aggregate_gbs"] * 1e9) + d2h_bytes / (d["d2h"]["aggregate_gbs"] * 1e9)) * 1e3
+    both_ms = (h2d_bytes + d2h_bytes) / (d["both"]["aggregate_gbs"] * 1e9) * 1e3
+    return {"h2d_gbs_per_gpu": d["h2d"]["per_gpu_gbs_each_direction"], "d2h_gbs_per_gpu": d["d2h"]["per_gpu_gbs_each_direction"],
+            "both_gbs_per_gpu_each_way": d["both"]["per_gpu_gbs_each_direction"], "copies_alone_ms_serial": serial_ms,
+            "copies_alone_ms_concurrent": both_ms, "source": f"profiles/pcie_peak_r02_g{g}.json"}
+
+
 def run_ours(args):
     import torch  # plumbing only: torch.distributed rendezvous / barrier / max-reduce, never on the compute path
 
@@ -862,6 +876,11 @@ def run_ours(args):
                           f"({r['tile']}x{r['tile']} tiles, vw {r['vw']}), OpenMP, {r['sec_per_call']:.2f} s/call"),
                "axpy_f32_gbs": cpu_reference_axpy(1 << 26, np.float32)}
 
+    if rank == 0 and e2e is not None:
+        hl = host_link_ceiling(g, e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"])
+        if hl is not None:
+            hl["step_ms_over_copies_alone"] = e2e["ms_per_step"] / min(hl["copies_alone_ms_serial"], hl["copies_alone_ms_concurrent"])
+            e2e["host_link"] = hl
     if rank == 0:
         line = {
             "metric": "gemm_f32_tflops", "value": tflops, "unit": "TFLOP/s", "n_gpus": g, "steps": args.steps,

@@ -72,6 +72,7 @@ struct Params {
     unsigned *tickets;
     int n_peers, self;
     int peer_bulk;  // fused all-gather: peers receive whole 128-byte row segments as bulk async copies from the staging tile
+    int peer_tma;   // fused all-gather: every finished 32 x 32 chunk leaves as ONE TMA store per rank (PeerMaps), self included
     float *peers[16];
     // A-prologue (Linear.backward, src/nn/layer/linear.zig:608-613 fused into the GEMM that consumes it): the A operand is
     // used as A o act'(Y), Y = the layer output with A's shape and layout; colsum (op_a = T only) receives the column sums
@@ -89,6 +90,12 @@ __device__ __forceinline__ void trace_stamp(const Params &p, int slot) {
         p.trace[(size_t)blockIdx.x * 16 + slot] = t;
     }
 }
+
+// fused all-gather through the TMA engine: one tensor map per rank's C (this rank's row block of it), self included
+constexpr int MAX_PEER_MAPS = 8;
+struct PeerMaps {
+    CUtensorMap m[MAX_PEER_MAPS];
+};
 
 struct Barriers {
     uint64_t raw_full[MAX_STAGES];    // TMA -> converters                      (own CTA)
@@ -153,7 +160,7 @@ template <int CTAS, bool PRE, bool PROL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
-                   const __grid_constant__ CUtensorMap tmC, const Params p) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ PeerMaps pm, const Params p) {
     static_assert(!(PRE && PROL), "the pre-split experiment has no prologue variant");
     using C = Cfg<CTAS, PROL>;  // PROL: tmAlo is the tensor map of Y
     constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RAW_BYTES = C::RAW_BYTES, A_BYTES = C::A_BYTES;
@@ -565,6 +572,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float *bias_p = p.bias;
             asm volatile("" : "+r"(box_lane), "+r"(swz), "+l"(tmc_addr), "+r"(f_alpha), "+r"(f_act), "+f"(alpha_v), "+l"(bias_p));
             const bool plain = !f_alpha && !f_act && bias_p == nullptr;
+            const int n_maps = p.peer_tma ? p.n_peers : 0;
             auto store_tma = [&](const uint32_t (&r)[32], int c, int n_chunk) {
                 const uint32_t box = box_lane + (n_chunk & 1) * 4096;
                 const bool tr = p.trace && c == 1 && q == 0 && lane == 0;
@@ -610,16 +618,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (tr) trace_stamp(p, 14);
                 if (lane == 0) {
                     const int32_t ccol = (int32_t)(col0 + (uint64_t)c * 32), crow = (int32_t)row0;
-                    if ((uint64_t)ccol < p.N && row0 < p.M)
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmc_addr),
-                                     "r"(ccol), "r"(crow), "r"(box - lane * 128)
-                                     : "memory");
+                    if ((uint64_t)ccol < p.N && row0 < p.M) {
+                        if (n_maps == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmc_addr),
+                                         "r"(ccol), "r"(crow), "r"(box - lane * 128)
+                                         : "memory");
+                        } else {
+                            // fused all-gather: the same staged box goes to every rank's C (own copy first), one TMA store each --
+                            // the NVLink transfer is issued by the copy engine while this warp moves on to the next chunk
+                            for (int i = 0; i < n_maps; i++) {
+                                const int dst = p.self + i < n_maps ? p.self + i : p.self + i - n_maps;
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&pm.m[dst])),
+                                             "r"(ccol), "r"(crow), "r"(box - lane * 128)
+                                             : "memory");
+                            }
+                        }
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (tr) trace_stamp(p, 15);
             };
             const bool local_only = p.n_peers == 0;
-            const bool use_tma_store = local_only && p.c_tma && !p.has_beta;
+            const bool use_tma_store = (local_only || p.peer_tma) && p.c_tma && !p.has_beta;
             int n_chunk = 0;
 
             if (p.splits == 1 || w < p.n_full) {
@@ -911,9 +932,20 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     static const int tma_store_env = env_int("WK_GEMM_TMA_STORE", 1);
     CUtensorMap tmC = tmA;
     p.c_tma = 0;
+    static PeerMaps pm_zero{};
+    PeerMaps pm = pm_zero;
+    p.peer_tma = 0;
     if (p.c_vec && tma_store_env && !(peers && peers->n > 1)) {
         // finished 32 x 32 chunks of C: 128-byte rows, swizzled staging box, clipped against [M, N] by the engine
         p.c_tma = make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, N, M, ldc * 4, 32, 32) ? 1 : 0;
+    } else if (p.c_vec && tma_store_env && peers && peers->n <= MAX_PEER_MAPS) {
+        // measured on 8 B200s in one session (profiles/bench_r02d_g8*.json): 1817 TF/s with one TMA store per (chunk, rank) against
+        // 1866 with the per-row bulk copies of the transposing path (compute-only 2006-2054) -- not a gain, so it stays opt-in
+        static const int peer_tma_env = env_int("WK_GEMM_PEER_TMA", 0);
+        bool all = peer_tma_env != 0;
+        for (int i = 0; i < peers->n && all; i++)
+            all = make_tmap_2d(&pm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, peers->ptrs[i], N, M, ldc * 4, 32, 32);
+        if (all) p.c_tma = p.peer_tma = 1;
     }
     p.has_alpha = (alpha != nullptr || beta != nullptr);
     p.has_beta = (beta != nullptr);
@@ -1052,13 +1084,13 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         cfg.attrs = attr;
         cfg.numAttrs = na;
         if (prolog) {
-            WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+            WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false, true>, tmA, tmB, tmAlo, tmBlo, tmC, pm, p));
         } else if (presplit) {
-            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
-            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, true>, tmA, tmB, tmAlo, tmBlo, tmC, pm, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, true>, tmA, tmB, tmAlo, tmBlo, tmC, pm, p));
         } else {
-            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, false>, tmA, tmB, tmAlo, tmBlo, tmC, p));
-            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false>, tmA, tmB, tmAlo, tmBlo, tmC, p));
+            if (ctas == 1) WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<1, false>, tmA, tmB, tmAlo, tmBlo, tmC, pm, p));
+            else WK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<2, false>, tmA, tmB, tmAlo, tmBlo, tmC, pm, p));
         }
     }
     WK_CHECK_LAUNCH();
