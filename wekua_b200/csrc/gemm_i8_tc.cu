@@ -260,45 +260,39 @@ gemm_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------- operand staging
-// Byte planes of a W-byte integer operand, K-major, every plane zero-padded to Kp (a multiple of 128) columns:
-//   dst[r][plane_slot * Kp + k] = byte `plane` of X(r, k),  X(r, k) = src[r * ld + k]  (TRANS = false)
-//                                                                   = src[k * ld + r]  (TRANS = true: op(X) is the stored X^T)
-// plane_slot = plane (ascending, operand A) or W - 1 - plane (descending, operand B).  One 32 x 32 element tile per block goes
-// through shared memory so that both the global reads and the byte-plane writes are coalesced for either orientation.
-template <int W, bool TRANS>
+// Byte planes of a W-byte integer operand X[R][K] (row-major, pitch ld elements), K-major, every plane zero-padded to Kp (a
+// multiple of 128) columns:   dst[r][plane_slot * Kp + k] = byte `plane` of X(r, k)
+// plane_slot = plane (ascending, operand A) or W - 1 - plane (descending, operand B).  A thread takes 16 consecutive k of one
+// row: 16 W bytes in (128-bit loads when the rows are 16-byte aligned), one 16-byte store per plane out -- 8 threads cover
+// 128 contiguous bytes of every plane row.  Transposed operands are transposed first (the 128-bit tiled transpose kernel).
+template <int W, bool VEC>
 __global__ void __launch_bounds__(256) split_planes_kernel(const uint8_t *__restrict__ src, uint64_t ld, uint64_t R, uint64_t K,
                                                            uint8_t *__restrict__ dst, uint64_t Kp, int descending) {
-    __shared__ uint8_t tile[32][32 * W + 4];
-    const uint64_t r0 = (uint64_t)blockIdx.y * 32, k0 = (uint64_t)blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    // load: the stored-contiguous index follows tx
+    using ElemT = typename UInt<W>::type;
+    const uint64_t r = (uint64_t)blockIdx.y * 32 + (threadIdx.x >> 3);
+    const uint64_t k = ((uint64_t)blockIdx.x * 8 + (threadIdx.x & 7)) * 16;
+    if (r >= R || k >= Kp) return;
+    union { uint4 v[W]; ElemT e[16]; } in;
+    const ElemT *s = reinterpret_cast<const ElemT *>(src) + r * ld + k;
+    if (VEC && k + 16 <= K) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int y = ty + j * 8;
-        const uint64_t r = TRANS ? r0 + tx : r0 + y, k = TRANS ? k0 + y : k0 + tx;
-        const bool in = r < R && k < K;
-        using ElemT = typename UInt<W>::type;
-        const uint64_t word = in ? (uint64_t)reinterpret_cast<const ElemT *>(src)[TRANS ? k * ld + r : r * ld + k] : 0ull;
+        for (int i = 0; i < W; i++) in.v[i] = __ldg(reinterpret_cast<const uint4 *>(s) + i);
+    } else {
 #pragma unroll
-        for (int b = 0; b < W; b++) {
-            const uint8_t v = (uint8_t)(word >> (8 * b));  // little endian: byte b = plane b
-            if (TRANS) tile[tx][y * W + b] = v;   // tile[row][k][byte]
-            else tile[y][tx * W + b] = v;
-        }
+        for (int i = 0; i < 16; i++) in.e[i] = k + i < K ? s[i] : (ElemT)0;
     }
-    __syncthreads();
-    // store: k follows tx in every plane
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int y = ty + j * 8;
-        const uint64_t r = r0 + y, k = k0 + tx;
-        if (r < R && k < Kp) {
+    for (int b = 0; b < W; b++) {
+        uint32_t w[4];
 #pragma unroll
-            for (int b = 0; b < W; b++) {
-                const int slot = descending ? W - 1 - b : b;
-                dst[r * (uint64_t)W * Kp + (uint64_t)slot * Kp + k] = tile[y][tx * W + b];
-            }
+        for (int jq = 0; jq < 4; jq++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) x |= (uint32_t)((in.e[jq * 4 + e] >> (8 * b)) & 0xff) << (8 * e);  // little endian: byte b = plane b
+            w[jq] = x;
         }
+        const int slot = descending ? W - 1 - b : b;
+        *reinterpret_cast<uint4 *>(dst + r * (uint64_t)W * Kp + (uint64_t)slot * Kp + k) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -344,15 +338,15 @@ static int32_t launch_u8(wk_queue *q, int ctas, const CUtensorMap &tmA, const CU
 }
 
 template <int W>
-static int32_t split_planes(wk_queue *q, bool trans, const void *src, uint64_t ld, uint64_t R, uint64_t K, void *dst, uint64_t Kp,
-                            int descending) {
+static int32_t split_planes(wk_queue *q, const void *src, uint64_t ld, uint64_t R, uint64_t K, void *dst, uint64_t Kp, int descending) {
     using namespace i8tc;
-    const dim3 grid((unsigned)((Kp + 31) / 32), (unsigned)((R + 31) / 32));
+    const dim3 grid((unsigned)((Kp + 127) / 128), (unsigned)((R + 31) / 32));
     if (grid.y > 65535) {  // 2M rows: not a GEMM this path is for
         set_error("gemm_int_tc: operand too tall");
         return WK_ERR_INVALID_VALUE;
     }
-    if (trans) split_planes_kernel<W, true><<<grid, 256, 0, q->stream>>>((const uint8_t *)src, ld, R, K, (uint8_t *)dst, Kp, descending);
+    const bool vec = aligned16(src) && (ld * W) % 16 == 0;
+    if (vec) split_planes_kernel<W, true><<<grid, 256, 0, q->stream>>>((const uint8_t *)src, ld, R, K, (uint8_t *)dst, Kp, descending);
     else split_planes_kernel<W, false><<<grid, 256, 0, q->stream>>>((const uint8_t *)src, ld, R, K, (uint8_t *)dst, Kp, descending);
     WK_CHECK_LAUNCH();
     return WK_OK;
@@ -370,31 +364,52 @@ static int32_t gemm_int_tc_w(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M
     static const int ctas_env = env_int_i8("WK_GEMM_CTAS", 0);
     const int ctas = ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1);
 
-    // operands in place (W = 1, K-major, 16-byte aligned rows) or staged as byte planes
+    // operands in place (W = 1, K-major, 16-byte aligned rows) or staged: byte planes [rows][W * Kp], K-major, zero-padded.
+    // A transposed operand (op(X) = stored X^T) is transposed first by the 128-bit tiled transpose kernel -- straight into its
+    // final place for W = 1 (one plane: the tensor map's bound K zero-fills the tail instead of padding), through a scratch
+    // matrix for wider elements.
     const bool a_direct = W == 1 && op_a == 0 && aligned16(A) && lda % 16 == 0;
     const bool b_direct = W == 1 && op_b == 1 && aligned16(B) && ldb % 16 == 0;
+    const bool a_trans = op_a == 1, b_trans = op_b == 0;
     const uint64_t Kp = (K + BKB - 1) / BKB * BKB;
-    const size_t a_bytes = a_direct ? 0 : ((size_t)M * W * Kp + 255) / 256 * 256;
-    const size_t b_bytes = b_direct ? 0 : (size_t)N * W * Kp;
+    const uint64_t per16 = 16 / W, Kt = (K + per16 - 1) / per16 * per16;  // element pitch of a transposed scratch matrix
+    auto al256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t a_bytes = a_direct ? 0 : al256((size_t)M * W * Kp), b_bytes = b_direct ? 0 : al256((size_t)N * W * Kp);
+    const size_t ta_bytes = (!a_direct && a_trans && W > 1) ? al256((size_t)M * Kt * W) : 0;
+    const size_t tb_bytes = (!b_direct && b_trans && W > 1) ? al256((size_t)N * Kt * W) : 0;
     const uint8_t *a_ptr = (const uint8_t *)A, *b_ptr = (const uint8_t *)B;
     uint64_t a_pitch = lda, b_pitch = ldb, a_inner = K, b_inner = K;
     if (a_bytes + b_bytes) {
-        if (q->int_ws_bytes < a_bytes + b_bytes) {
-            int32_t rc = grow_buffer(q, &q->int_ws, &q->int_ws_bytes, a_bytes + b_bytes);
+        const size_t need = a_bytes + b_bytes + ta_bytes + tb_bytes;
+        if (q->int_ws_bytes < need) {
+            int32_t rc = grow_buffer(q, &q->int_ws, &q->int_ws_bytes, need);
             if (rc != WK_OK) return rc;
         }
+        constexpr int32_t size_dtype = W == 1 ? 1 : W == 2 ? 3 : W == 4 ? 5 : 7;  // an unsigned dtype id of W bytes (transpose by size)
+        auto stage = [&](const void *X, uint64_t ldx, uint64_t rows, bool trans, uint8_t *dst, uint8_t *scratch, int descending) -> int32_t {
+            if (trans && W == 1) return wk_transpose2d(q, size_dtype, K, rows, X, ldx, dst, Kp);  // stored [K][rows] -> [rows][Kp]
+            if (trans) {
+                int32_t rc = wk_transpose2d(q, size_dtype, K, rows, X, ldx, scratch, Kt);
+                if (rc != WK_OK) return rc;
+                return split_planes<W>(q, scratch, Kt, rows, K, dst, Kp, descending);
+            }
+            return split_planes<W>(q, X, ldx, rows, K, dst, Kp, descending);
+        };
+        uint8_t *ws = (uint8_t *)q->int_ws;
         if (!a_direct) {
-            int32_t rc = split_planes<W>(q, op_a == 1, A, lda, M, K, q->int_ws, Kp, 0);
+            int32_t rc = stage(A, lda, M, a_trans, ws, ws + a_bytes + b_bytes, 0);
             if (rc != WK_OK) return rc;
-            a_ptr = (const uint8_t *)q->int_ws;
-            a_pitch = a_inner = (uint64_t)W * Kp;
+            a_ptr = ws;
+            a_pitch = (uint64_t)W * Kp;
+            a_inner = (W == 1 && a_trans) ? K : a_pitch;  // (transposed 8-bit operand: columns [K, Kp) were not written)
         }
         if (!b_direct) {
-            uint8_t *dst = (uint8_t *)q->int_ws + a_bytes;
-            int32_t rc = split_planes<W>(q, op_b == 0, B, ldb, N, K, dst, Kp, 1);
+            uint8_t *dst = ws + a_bytes;
+            int32_t rc = stage(B, ldb, N, b_trans, dst, ws + a_bytes + b_bytes + ta_bytes, 1);
             if (rc != WK_OK) return rc;
             b_ptr = dst;
-            b_pitch = b_inner = (uint64_t)W * Kp;
+            b_pitch = (uint64_t)W * Kp;
+            b_inner = (W == 1 && b_trans) ? K : b_pitch;
         }
     }
     CUtensorMap tmA, tmB;
