@@ -49,3 +49,19 @@ def test_reference_arm_under_torchrun_env_uses_all_cores_and_our_config():
     assert line["ms_per_step"] * 3 < 4000 * 2  # the sample was sized to the budget
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(env, RANK="1"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_reads_roofline_inputs_from_committed_profiles():
+    """roofline.traffic comes from the committed ncu summary whose kernel NAME matches the HEAD kernel (not a constant), and the
+    e2e host-link ceiling from the committed PCIe measurements"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    t = bench.ncu_traffic_bytes("gemm_f32_n32768_1gpu")
+    assert t is not None and 1.5e11 < t < 1.9e11  # 163 GB read + 4.6 GB written per launch at N = 32768
+    for key in ("axpy_f32_2^28", "axpy_f64_2^28"):
+        assert bench.ncu_traffic_bytes(key) is not None
+    assert bench.ncu_traffic_bytes("no_such_kernel") is None
+    hl = bench.host_link_ceiling(8, 2 * 32768 ** 2 * 4, 32768 ** 2 * 4)
+    assert hl is not None and 60 < hl["copies_alone_ms_serial"] < 150 and hl["source"].endswith("pcie_peak_r02_g8.json")
+    assert bench.host_link_ceiling(3, 1, 1) is None  # no measurement for 3 GPUs: no ceiling claimed

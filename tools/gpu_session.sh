@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_int_tc.py tests/test_gpu_complex.py -x -q 2>&1 | tail -4
-timeout 600 python tools/gemm_int_sweep.py gpurun_out/sweep_gemm_int_r02c > gpurun_out/sweep_int_c.log 2>&1
-cat gpurun_out/sweep_gemm_int_r02c.md | head -20
+for cfg in "2 16" "4 16" "4 8" "8 8" "8 4"; do set -- $cfg; echo "NJ=$1 PANELS=$2"; WK_E2E_NJ=$1 WK_E2E_PANELS=$2 python bench.py --steps 5 --warmup 3 --quick --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'ms',round(d['e2e']['ms_per_step'],1))"; done
