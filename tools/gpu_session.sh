@@ -1,4 +1,7 @@
 cd $GRAFT_REPO_ROOT
-for cfg in "2 16" "4 16" "4 8" "8 8" "8 4"; do set -- $cfg; echo "NJ=$1 PANELS=$2"; WK_E2E_NJ=$1 WK_E2E_PANELS=$2 python bench.py --steps 5 --warmup 3 --quick --no-cpu 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'ms',round(d['e2e']['ms_per_step'],1))"; done
+S="128 128 128 256 256 256 384 384 384 512 512 512 256 1024 256"
+python tools/gemm_small_time.py f32 $S
+python tools/gemm_small_time.py f64 $S
+WK_GEMM_PATH=simt python tools/gemm_small_time.py f32 512 512 512 768 768 768
+WK_GEMM_PATH=simt python tools/gemm_small_time.py f64 768 768 768
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_xor.py tests/test_gpu_complex.py -x -q 2>&1 | tail -3

@@ -11,6 +11,14 @@
 
 #include "common.cuh"
 
+// cross-over of the small-tile SIMT kernel against the tensor-core kernels, in multiply-adds (measured: profiles/small_gemm_f32_r02.txt)
+#ifndef WK_SMALL_SIMT_F32
+#define WK_SMALL_SIMT_F32 7.0e7  /* ~400^3: 256^3 9.8 us against 15.9 on the tensor cores, 512^3 23.8 against 16.5 */
+#endif
+#ifndef WK_SMALL_SIMT_F64
+#define WK_SMALL_SIMT_F64 1.4e8  /* ~512^3: 256^3 12.7 us against 42.5 on DMMA (four 128 x 128 tiles), 768^3 101 against 49 */
+#endif
+
 namespace wk {
 static int g_gemm_path = 0;  // 0 auto, 1 SIMT, 2 tensor-core (fail if not eligible)
 
@@ -65,7 +73,16 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
         return WK_ERR_INVALID_VALUE;
     }
     const int path = gemm_path();
-    if (path != 1 && (dtype == 8 || dtype == 9)) {
+    // Launch-bound float problems: the tensor-core kernels carry ~15 us of fixed cost (cluster launch, TMEM, pipeline fill, split-K
+    // exchange), the small-tile SIMT kernel ~3 us -- below the measured cross-over it is simply faster, and exact fp32 / fp64 FMA
+    // arithmetic on top (thresholds in multiply-adds; WK_GEMM_SMALL_SIMT_F32 / _F64 override, 0 disables)
+    static const double small_f32 = [] { const char *e = getenv("WK_GEMM_SMALL_SIMT_F32"); return e && *e ? atof(e) : WK_SMALL_SIMT_F32; }();
+    static const double small_f64 = [] { const char *e = getenv("WK_GEMM_SMALL_SIMT_F64"); return e && *e ? atof(e) : WK_SMALL_SIMT_F64; }();
+    const double macs = (double)M * (double)N * (double)K;
+    // (the SIMT kernel has no split-K: long-K / few-tile shapes such as 64 x 512 x 4096 stay on the tensor cores)
+    const bool small_float = path == 0 && !(peers && peers->n > 1) &&
+                             ((dtype == 8 && macs <= small_f32 && K <= 512) || (dtype == 9 && macs <= small_f64 && K <= 1024));
+    if (path != 1 && !small_float && (dtype == 8 || dtype == 9)) {
         const size_t es = dtype_size(dtype), per16 = 16 / es;
         const uint64_t a_rows = op_a ? K : M, b_rows = op_b ? N : K;
         const bool a_bad = !aligned16(A) || lda % per16, b_bad = !aligned16(B) || ldb % per16;
