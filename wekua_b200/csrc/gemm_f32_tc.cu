@@ -58,6 +58,7 @@ struct Params {
     const float *bias;
     int act;
     int op_a, op_b;
+    int a_mn3d, b_mn3d;  // MN-major operand loaded as ONE 3-D TMA box per stage instead of 4-8 32 x 32 boxes (MN % 32 == 0)
     int c_vec;  // C rows are 16-byte aligned: 128-bit epilogue accesses
     int c_tma;  // ... and C has a tensor map: finished 32 x 32 chunks leave through TMA stores
     int split;  // 0: store hi = rna_tf32(x) explicitly; 1: leave x in place, the tensor core truncates; 2: rounds
@@ -235,11 +236,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         uint8_t *ad = a_dst + plane * RAW_BYTES, *bd = b_dst + plane * RAW_BYTES;
                         if (p.op_a == 0) {  // A[M][K]: one 32(k) x 128(m) box, K-major
                             tma_load_2d(ad, ma, k0, m0, &bars->raw_full[s]);
+                        } else if (p.a_mn3d && !plane) {  // A[K][M], M % 32 == 0: one (32, 32 k, 4 chunks) box
+                            tma_load_3d(ad, ma, 0, k0, m0 / 32, &bars->raw_full[s]);
                         } else {            // A[K][M]: four 32(m) x 32(k) boxes, MN-major
                             for (int j = 0; j < BM / 32; j++) tma_load_2d(ad + j * 4096, ma, m0 + 32 * j, k0, &bars->raw_full[s]);
                         }
                         if (p.op_b == 1) {  // B[N][K]: one 32(k) x BN_LOAD(n) box, K-major
                             tma_load_2d(bd, mb, k0, n0, &bars->raw_full[s]);
+                        } else if (p.b_mn3d && !plane) {  // B[K][N], N % 32 == 0: one (32, 32 k, BN_LOAD / 32 chunks) box
+                            tma_load_3d(bd, mb, 0, k0, n0 / 32, &bars->raw_full[s]);
                         } else {            // B[K][N]: 32(n) x 32(k) boxes, MN-major
                             for (int j = 0; j < C::BN_LOAD / 32; j++) tma_load_2d(bd + j * 4096, mb, n0 + 32 * j, k0, &bars->raw_full[s]);
                         }
@@ -887,6 +892,14 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
         set_error("gemm_f32_tc: cuTensorMapEncodeTiled failed");
         return WK_ERR_CUDA;
     }
+    // MN-major operands whose MN extent is a multiple of 32: one 3-D box per stage instead of BM / 32 (+ BN_LOAD / 32) 2-D ones
+    static const int mn3d_env = env_int("WK_GEMM_MN3D", 1);
+    int a_mn3d = 0, b_mn3d = 0;
+    if (mn3d_env && !prolog) {
+        CUtensorMap t3;
+        if (op_a == 1 && M % 32 == 0 && make_tmap_mn_chunks(&t3, A, M, K, lda * 4, BK, BM / 32)) { tmA = t3; a_mn3d = 1; }
+        if (op_b == 0 && N % 32 == 0 && make_tmap_mn_chunks(&t3, B, N, K, ldb * 4, BK, bn_load / 32)) { tmB = t3; b_mn3d = 1; }
+    }
     // WK_GEMM_PRESPLIT=1 (experimental, off by default): lo planes computed in one streaming pass per operand and loaded by
     // TMA, so the converter warps move no shared memory.  Costs an operand-sized workspace and 2x the L2 -> SM traffic.
     static const int presplit_env = env_int("WK_GEMM_PRESPLIT", 0);
@@ -954,6 +967,7 @@ int32_t gemm_f32_tc(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M, uint64_
     p.bias = bias;
     p.act = act;
     p.op_a = op_a; p.op_b = op_b;
+    p.a_mn3d = a_mn3d; p.b_mn3d = b_mn3d;
     p.split = split_env;
     p.tiles_m = (uint32_t)((M + (uint64_t)BM * ctas - 1) / ((uint64_t)BM * ctas));
     p.tiles_n = (uint32_t)((N + BN - 1) / BN);

@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1, int32_t c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
 // same, but the data lands at the same smem offset and signals the same barrier offset in CTA `cta` of the pair
 __device__ __forceinline__ void tma_load_2d_cta_group2(void *smem_dst, const CUtensorMap *m, int32_t c0, int32_t c1,
                                                        uint64_t *bar_leader_mapped_addr_holder, uint32_t bar_addr_cluster) {
@@ -283,6 +290,24 @@ inline bool make_tmap_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *b
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// MN-major operand X[K][MN] (MN contiguous, row pitch `pitch_bytes`) seen as a 3-D tensor [MN / 32][K][32]: a box of
+// (32, box_k, n_chunks) lands in shared memory as n_chunks consecutive [box_k][32] blocks of 128-byte rows -- exactly the layout
+// of n_chunks separate 32 x box_k boxes, in ONE instruction.  Only for MN a multiple of 32 (a partial last chunk would read the
+// next row).
+inline bool make_tmap_mn_chunks(CUtensorMap *map, const void *base, uint64_t mn, uint64_t k, uint64_t pitch_bytes, uint32_t box_k,
+                                uint32_t n_chunks) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc || mn % 32) return false;
+    cuuint64_t dims[3] = {32, k, mn / 32};
+    cuuint64_t strides[2] = {pitch_bytes, 128};
+    cuuint32_t box[3] = {32, box_k, n_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
