@@ -438,9 +438,8 @@ static int32_t gemm_int_tc_w(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M
     p.group_m = 16;
 
     // passes: byte-plane group s = all pairs (A_i, B_j) with i + j = s.  With A's planes ascending and B's descending in their
-    // rows, the group is ONE contiguous k-range of (s + 1) * Kp bytes in both operands; when that exceeds what an s32
-    // accumulator can take (32768 products), the pairs are walked one by one in chunks of 32768.  (W = 1: one plane, slot 0,
-    // whether the operand is used in place or staged.)
+    // rows, the group is ONE contiguous k-range of (s + 1) * Kp bytes in both operands, cut into pieces of at most 32768
+    // products (what an s32 accumulator takes).  (W = 1: one plane, slot 0, whether the operand is used in place or staged.)
     bool first = true;
     auto launch = [&](uint64_t a_off, uint64_t b_off, uint64_t len, int s) -> int32_t {
         p.a_k0 = (int32_t)a_off;
@@ -456,18 +455,14 @@ static int32_t gemm_int_tc_w(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M
         return launch_u8<W>(q, ctas, tmA, tmB, p);
     };
     for (int s = 0; s < W; s++) {
-        const uint64_t planes = (uint64_t)s + 1;
-        if (planes * Kp <= MAX_K_PER_LAUNCH) {
-            int32_t rc = launch(0, (uint64_t)(W - 1 - s) * Kp, planes * Kp, s);
+        // the group's k-range: planes 0..s of A (from byte 0) against planes s..0 of B (from slot W - 1 - s), position by position --
+        // so ANY contiguous piece of it is a valid partial sum, and pieces of <= 32768 products keep the s32 accumulator exact
+        const uint64_t total = ((uint64_t)s + 1) * Kp, b_base = (uint64_t)(W - 1 - s) * Kp;
+        for (uint64_t k_lo = 0; k_lo < total; k_lo += MAX_K_PER_LAUNCH) {
+            const uint64_t len = total - k_lo < MAX_K_PER_LAUNCH ? total - k_lo : MAX_K_PER_LAUNCH;
+            int32_t rc = launch(k_lo, b_base + k_lo, len, s);
             if (rc != WK_OK) return rc;
-            continue;
         }
-        for (int i = 0; i <= s; i++)  // pair (A_i, B_{s-i}): slot i of A, slot W - 1 - (s - i) of B
-            for (uint64_t k_lo = 0; k_lo < Kp; k_lo += MAX_K_PER_LAUNCH) {
-                const uint64_t len = Kp - k_lo < MAX_K_PER_LAUNCH ? Kp - k_lo : MAX_K_PER_LAUNCH;
-                int32_t rc = launch((uint64_t)i * Kp + k_lo, (uint64_t)(W - 1 - (s - i)) * Kp + k_lo, len, s);
-                if (rc != WK_OK) return rc;
-            }
     }
     return WK_OK;
 }
