@@ -79,6 +79,8 @@ struct CommandQueue {  // src/core/command_queue.zig:10-28
 struct Context {  // src/core/context.zig:13-190
     wk_context *handle = nullptr;
     std::vector<CommandQueue> command_queues;
+    // tensors that outlive their Context must not touch it in their destructor: they hold this token and check it
+    std::shared_ptr<bool> alive = std::make_shared<bool>(true);
 
     static std::unique_ptr<Context> init(const std::vector<int32_t> &device_ordinals) {  // Context.init :13
         std::unique_ptr<Context> c(new Context());
@@ -93,6 +95,7 @@ struct Context {  // src/core/context.zig:13-190
         return c;
     }
     ~Context() {
+        *alive = false;
         if (handle) wk_context_destroy(handle);
     }
 
@@ -150,6 +153,7 @@ struct CreateConfig {  // src/tensor/main.zig:35-39
 
 template <typename T> struct Tensor {  // src/tensor/main.zig:62-279
     Context *context = nullptr;
+    std::shared_ptr<bool> context_alive;
     void *buffer = nullptr;
     std::vector<uint64_t> shape, pitches;
     uint64_t depth = 1, rows = 1, rows_padded = 2, cols = 1;
@@ -164,6 +168,7 @@ template <typename T> struct Tensor {  // src/tensor/main.zig:62-279
             if (s == 0) fail(WK_ERR_INVALID_VALUE);
         std::unique_ptr<Tensor> t(new Tensor());
         t->context = ctx;
+        t->context_alive = ctx->alive;
         t->shape = shape;
         uint64_t vw = 1;
         if (cfg.vectors_enabled)
@@ -206,8 +211,8 @@ template <typename T> struct Tensor {  // src/tensor/main.zig:62-279
         if (buffer) check(wk_free(p->q(), buffer));
         buffer = nullptr;
     }
-    ~Tensor() {
-        if (buffer && context && !context->command_queues.empty()) wk_free(context->command_queues[0].handle, buffer);
+    ~Tensor() {  // the reference requires release(pipeline); a tensor dropped without it frees its buffer only while its Context lives
+        if (buffer && context_alive && *context_alive && !context->command_queues.empty()) wk_free(context->command_queues[0].handle, buffer);
     }
     uint64_t pitchSum() const {
         uint64_t s = 0;
