@@ -4,8 +4,9 @@
 //   f64  -> FP64 tensor-core MMA (DMMA)                                      (gemm_f64_tc.cu)
 //   ints -> tcgen05.mma kind::i8 over byte planes, exact mod 2^bits          (gemm_i8_tc.cu)
 //           small problems: SIMT, wrap-around arithmetic, bit-exact          (gemm_simt.cu)
-// A float problem whose layout cannot feed the tensor-core loaders (pointer / pitch not 16-byte aligned) takes the
-// SIMT kernel as well.  There is no CPU path.
+//   launch-bound float problems: small-tile SIMT kernel below the measured cross-over             (gemm_simt.cu)
+// A float operand whose layout cannot feed the tensor-core loaders (pointer / pitch not 16-byte aligned) is first copied
+// into an aligned scratch (stage_aligned).  There is no CPU path.
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,7 +50,6 @@ static int32_t stage_aligned(wk_queue *q, size_t es, const void **ptr, uint64_t 
     const uint64_t new_ld = (cols + per16 - 1) / per16 * per16;
     char *dst = (char *)q->align_ws + *offset;
     WK_CUDA(cudaMemcpy2DAsync(dst, new_ld * es, *ptr, *ld * es, cols * es, rows, cudaMemcpyDeviceToDevice, q->stream));
-    count_launch();
     *offset += ((size_t)rows * new_ld * es + 255) / 256 * 256;
     *ptr = dst;
     *ld = new_ld;

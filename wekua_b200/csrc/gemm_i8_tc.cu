@@ -360,7 +360,7 @@ static int32_t gemm_int_tc_w(wk_queue *q, int32_t op_a, int32_t op_b, uint64_t M
     using namespace i8tc;
     using namespace tc;
     if (q->prop.major != 10) return -1;
-    if (M > 0x7fffffffULL || N > 0x7fffffffULL || K * W > 0x7fffffffULL) return -1;
+    if (M > 0x7fffffffULL || N > 0x7fffffffULL || (K + 127) * W > 0x7fffffffULL) return -1;  // (k-byte offsets are int32 TMA coordinates)
     static const int ctas_env = env_int_i8("WK_GEMM_CTAS", 0);
     const int ctas = ctas_env == 1 || ctas_env == 2 ? ctas_env : (M > BM ? 2 : 1);
 
