@@ -354,28 +354,73 @@ template <typename T> struct AdamF {  // textbook Adam (Kingma & Ba alg. 1); v =
     }
 };
 
-// uniform.cl:32-54 (little-endian branch; `seed2 << 32` is always 0; `*` binds tighter than `^`)
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+// uniform.cl:32-54 (little-endian branch; `seed2 << 32` is always 0; `*` binds tighter than `^`), spelled out on 32-bit
+// halves.  The hash is the whole cost of the kernel (an f32 element is 4 bytes of HBM against ~25 integer instructions, and
+// the shift / logic pipe and the multiply pipe each retire 16 lanes per SM sub-partition and clock), so every instruction
+// counts and the two pipes are balanced:
+//   * combined = (idx_lo << 32) + idx_hi puts the HIGH index word (0 for any tensor below 2^32 elements) into the LOW half
+//     of x0, so every term that only depends on x0_lo is an invariant (XxhInv): the x0_lo parts of both rotations, and the
+//     x0_lo part of rotl(x0, 24) * C (rotations are linear over disjoint bit fields: rotl(x0,24) = var + const);
+//   * x * C mod 2^64 is one widening multiply-add plus two 32-bit multiply-adds into the high word (the `<< 24` of the
+//     variable part folds into the constant C_LO << 24);
+//   * (x1 >> 35) + 8 fits 32 bits: its product with C is one widening multiply-add (the "+ 8" rides along as the 64-bit
+//     addend 8 * C) plus one multiply-add;
+//   * right shifts of a 32-bit word are written as mul.hi by a power of two (multiply pipe) where that balances the pipes.
+// Same arithmetic mod 2^64, bit for bit (tests/test_gpu_parity.py pins it on the oracle's 64-bit restatement).
+struct XxhInv { uint32_t key_hi, kk, k_lo, mc_lo, mc_hi; };
+__device__ __forceinline__ uint64_t wk_xxhash64_key(uint64_t seed) { return (0x7C01812CF721AD1CULL ^ 0xDED46DE9839097DBULL) - seed; }
+__device__ __forceinline__ XxhInv wk_xxhash64_inv(uint32_t idx_hi, uint32_t key_lo, uint32_t key_hi) {
+    const uint32_t x0_lo = idx_hi ^ key_lo;
+    const uint64_t mc = (((uint64_t)(x0_lo >> 8) << 32) | (uint32_t)(x0_lo << 24)) * 0x9FB21C651E98DF25ULL;  // const part of rotl(x0,24) * C
+    return XxhInv{key_hi, key_hi ^ (x0_lo << 17), x0_lo ^ (x0_lo >> 15), (uint32_t)mc, (uint32_t)(mc >> 32)};
+}
+__device__ __forceinline__ void wk_xxhash64_elem(uint32_t idx_lo, const XxhInv &k, uint32_t &h_lo, uint32_t &h_hi) {
+    constexpr uint32_t C_LO = 0x1E98DF25u, C_HI = 0x9FB21C65u, C_LO24 = C_LO << 24;
+    constexpr uint64_t C8 = 8ULL * 0x9FB21C651E98DF25ULL;
+    const uint32_t x0_hi = idx_lo ^ k.key_hi;  // x0 = combined ^ key; x0_lo lives in the invariants
+    const uint32_t t = idx_lo ^ k.kk;          // x0_hi ^ (x0_lo << 17)
+    const uint32_t v = __umulhi(x0_hi, 1u << 24);  // x0_hi >> 8: low word of the variable part of rotl(x0, 24)
+    const uint64_t m = (uint64_t)v * C_LO + (((uint64_t)k.mc_hi << 32) | k.mc_lo);
+    const uint32_t m_hi = (uint32_t)(m >> 32) + v * C_HI + x0_hi * C_LO24;
+    const uint32_t x1_lo = k.k_lo ^ (x0_hi << 17) ^ (uint32_t)m;          // x0 ^ rotl(x0, 49) ^ rotl(x0, 24) * C
+    const uint32_t x1_hi = t ^ __umulhi(x0_hi, 1u << 17) ^ m_hi;          // (x0_hi >> 15)
+    const uint32_t s = x1_hi >> 3;                                        // x1 >> 35
+    const uint64_t p = (uint64_t)s * C_LO + C8;
+    const uint32_t p_hi = (uint32_t)(p >> 32) + s * C_HI;
+    const uint32_t x2_lo = x1_lo ^ (uint32_t)p, x2_hi = x1_hi ^ p_hi;
+    h_lo = x2_lo ^ __funnelshift_r(x2_lo, x2_hi, 28);  // x2 ^ (x2 >> 28)
+    h_hi = x2_hi ^ (x2_hi >> 28);
+}
+__device__ __forceinline__ void wk_xxhash64_halves(uint32_t idx_lo, uint32_t idx_hi, uint32_t key_lo, uint32_t key_hi, uint32_t &h_lo,
+                                                   uint32_t &h_hi) {
+    wk_xxhash64_elem(idx_lo, wk_xxhash64_inv(idx_hi, key_lo, key_hi), h_lo, h_hi);
+}
 __device__ __forceinline__ uint64_t wk_xxhash64(uint64_t index, uint64_t seed) {
-    const uint64_t key = (0x7C01812CF721AD1CULL ^ 0xDED46DE9839097DBULL) - seed;
-    const uint64_t combined = ((index & 0xFFFFFFFFULL) << 32) + (index >> 32);
-    const uint64_t x0 = combined ^ key;
-    const uint64_t x1 = x0 ^ rotl64(x0, 49) ^ (rotl64(x0, 24) * 0x9FB21C651E98DF25ULL);
-    const uint64_t x2 = x1 ^ (((x1 >> 35) + 8) * 0x9FB21C651E98DF25ULL);
-    return x2 ^ (x2 >> 28);
+    const uint64_t key = wk_xxhash64_key(seed);
+    uint32_t lo, hi;
+    wk_xxhash64_halves((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)key, (uint32_t)(key >> 32), lo, hi);
+    return ((uint64_t)hi << 32) | lo;
 }
 
-template <typename T, bool RANGE> __device__ __forceinline__ T uniform_value(uint64_t h, T min_value, T range) {
+// (T)h for the 64-bit hash h = hi:lo.  Measured dead ends (profiles/uniform_r02.md): replacing the 64-bit I2F by exact 32-bit
+// forms (double: two conversions + one FMA; float: hi | sticky through I2FP with a rare 64-bit fallback) costs more integer
+// instructions than the conversion unit saves -- the kernel is bound by the multiply (FMA-heavy) and logic pipes, not by XU.
+__device__ __forceinline__ double wk_u64_to_double(uint32_t lo, uint32_t hi) { return (double)(((uint64_t)hi << 32) | lo); }
+__device__ __forceinline__ float wk_u64_to_float(uint32_t lo, uint32_t hi) { return (float)(((uint64_t)hi << 32) | lo); }
+template <typename T, bool RANGE> __device__ __forceinline__ T uniform_value(uint32_t lo, uint32_t hi, T min_value, T range) {
     if (RANGE) {
-        // cl_khr_fp64 branch: (double)h / ULONG_MAX; ULONG_MAX converts to 2^64
-        const double normalized = (double)h / 18446744073709551616.0;
+        // cl_khr_fp64 branch: (double)h / ULONG_MAX; ULONG_MAX converts to 2^64 (a power of two: the division is an exact scaling)
+        const double normalized = wk_u64_to_double(lo, hi) * 0x1p-64;
         return (T)((double)min_value + normalized * (double)range);
     } else if (std::is_same<T, float>::value) {
-        return (T)((float)h / 18446744073709551616.0f);
+        return (T)(wk_u64_to_float(lo, hi) * 0x1p-64f);  // (float)h / 2^64f
     } else if (std::is_same<T, double>::value) {
-        return (T)((double)h / 18446744073709551616.0);
+        return (T)(wk_u64_to_double(lo, hi) * 0x1p-64);
     }
-    return (T)h;  // & WK_UINT_MAX == truncation
+    return (T)(((uint64_t)hi << 32) | lo);  // & WK_UINT_MAX == truncation
+}
+template <typename T, bool RANGE> __device__ __forceinline__ T uniform_value(uint64_t h, T min_value, T range) {
+    return uniform_value<T, RANGE>((uint32_t)h, (uint32_t)(h >> 32), min_value, range);
 }
 
 template <typename T, bool RANGE> struct UniformF {  // uniform.cl:56-185, idx = padded linear index
@@ -396,6 +441,51 @@ template <typename BT, bool RANGE> struct UniformF<Cx<BT>, RANGE> {
         v[0].im = uniform_value<BT, RANGE>(wk_xxhash64((idx << 1) + 1, seed), min_value, range);
     }
 };
+
+// Dense tensors (padded index == dense index) of a real base type: one thread per 16-byte vector, the index halves and the key
+// stay in 32-bit registers, nothing is read.  A complex tensor is the same stream over its base type: its components hash
+// (index << 1) and (index << 1) + 1 (uniform.cl:80-93), i.e. the flat index of the component.
+template <typename T, bool RANGE, bool SMALL>  // SMALL: n <= 2^32, the high index word is 0 and the invariants are per thread
+__global__ void __launch_bounds__(kThreads) uniform_dense_kernel(T *__restrict__ out, uint64_t n, uint32_t key_lo, uint32_t key_hi,
+                                                                 T min_value, T range) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    union Pack { uint4 u; T e[VEC]; };
+    const uint64_t n_vec = n / VEC;
+    XxhInv inv = wk_xxhash64_inv(0, key_lo, key_hi);
+    for (uint64_t vi = (uint64_t)blockIdx.x * kThreads + threadIdx.x; vi < n_vec; vi += (uint64_t)gridDim.x * kThreads) {
+        const uint64_t i0 = vi * VEC;
+        const uint32_t i_lo = (uint32_t)i0;
+        if (!SMALL) inv = wk_xxhash64_inv((uint32_t)(i0 >> 32), key_lo, key_hi);
+        Pack pk;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            uint32_t lo, hi;
+            wk_xxhash64_elem(i_lo | (uint32_t)e, inv, lo, hi);  // (i0 is a multiple of VEC)
+            pk.e[e] = uniform_value<T, RANGE>(lo, hi, min_value, range);
+        }
+        st_na(reinterpret_cast<uint4 *>(out) + vi, pk.u);
+    }
+    if (blockIdx.x == 0 && n_vec * VEC + threadIdx.x < n) {  // tail: fewer than VEC elements
+        const uint64_t i = n_vec * VEC + threadIdx.x;
+        uint32_t lo, hi;
+        wk_xxhash64_halves((uint32_t)i, (uint32_t)(i >> 32), key_lo, key_hi, lo, hi);
+        out[i] = uniform_value<T, RANGE>(lo, hi, min_value, range);
+    }
+}
+template <typename T, bool RANGE>
+static int32_t launch_uniform_dense(wk_queue *q, T *out, uint64_t n, uint64_t seed, T min_value, T range) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const uint64_t key = (0x7C01812CF721AD1CULL ^ 0xDED46DE9839097DBULL) - seed;
+    uint64_t blocks = (n / VEC + kThreads - 1) / kThreads;
+    const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+    blocks = blocks == 0 ? 1 : (blocks > cap ? cap : blocks);
+    if (n <= (1ull << 32))
+        uniform_dense_kernel<T, RANGE, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>(out, n, (uint32_t)key, (uint32_t)(key >> 32), min_value, range);
+    else
+        uniform_dense_kernel<T, RANGE, false><<<(unsigned)blocks, kThreads, 0, q->stream>>>(out, n, (uint32_t)key, (uint32_t)(key >> 32), min_value, range);
+    WK_CHECK_LAUNCH();
+    return WK_OK;
+}
 
 // bias.cl:3-19: out[i] += bias[i % row_pitch], i < n.  Flat streaming over the buffer like map_vec_kernel (128-bit
 // accesses, kBiasUnroll vectors of `out` in flight per thread -- only `out` comes from DRAM, so it needs a deeper
@@ -732,16 +822,21 @@ WK_API int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t r
         using base_t = typename IsCx<scalar_t>::base;  // min / max / range are scalars of the base type (uniform.zig:64-65)
         Ptrs<1> p{{buf}};
         Pitches<1> pit{{rp}, {sp}};
-        // the hash is taken over the PADDED linear index (uniform.cl:73): the dense fast path is only valid when
-        // padded index == dense index, which launch_map3d's density test guarantees.
+        // the hash is taken over the PADDED linear index (uniform.cl:73): the dense fast paths are only valid when
+        // padded index == dense index (the same density test as launch_map3d's).
+        const bool row_dense = rows == 1 || rp == cols;
+        const bool dense = buf && depth && rows && cols && row_dense && (depth == 1 || sp == rows * cols) && aligned16(buf);
+        constexpr uint64_t per_elem = sizeof(scalar_t) / sizeof(base_t);  // 2 for complex: the flat component index is what hashes
         if (minp || maxp) {
             // uniform.zig:96-106: missing bound = type min / max (floats: -floatMax / floatMax); range = max - min in T
             base_t mn = std::numeric_limits<base_t>::lowest(), mx = std::numeric_limits<base_t>::max();
             if (minp) mn = *(const base_t *)minp;
             if (maxp) mx = *(const base_t *)maxp;
             const base_t range = (base_t)(mx - mn);
+            if (dense) return launch_uniform_dense<base_t, true>(q, (base_t *)buf, depth * rows * cols * per_elem, seed, mn, range);
             return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, true>{seed, mn, range});
         }
+        if (dense) return launch_uniform_dense<base_t, false>(q, (base_t *)buf, depth * rows * cols * per_elem, seed, 0, 0);
         return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, UniformF<scalar_t, false>{seed, 0, 0});
     });
 }
