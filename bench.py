@@ -829,7 +829,7 @@ def run_ours(args):
         spec = importlib.util.spec_from_file_location("wk_stream_sweep", os.path.join(ROOT, "tools", "stream_sweep.py"))
         sw = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(sw)
-        rows_, _ = sw.sweep(27, only=("scal,hadamard (math.dot),sum,dot_reduce,sigmoid,tanh,sigmoid_dev,tanh_dev,"
+        rows_, _ = sw.sweep(27, only=("scal,hadamard (math.dot),sum,sum (device scalar),dot_reduce,sigmoid,tanh,sigmoid_dev,tanh_dev,"
                                       "act_backward(sigmoid),bias_add,bias_step,mse (+dev),gdm,adagrad,rmsprop,adam"),
                             ctx=ctx, pipe=pipe, reps=10, warm=3, verbose=False)
         layer_step = [{"op": r_["op"], "dtype": r_["dtype"], "bytes_per_elem": r_["bytes_per_elem"], "gbs": round(r_["gbs"], 1),

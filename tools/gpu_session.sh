@@ -1,4 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for c in 0 1 2; do echo "== WK_UNIFORM_CONV=$c"; WK_UNIFORM_CONV=$c WK_SWEEP_ONLY=uniform python tools/stream_sweep.py gpurun_out/sweep_uni_c$c 27 2>&1 | tail -2; done
-for c in 1 2; do WK_UNIFORM_CONV=$c timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stream_kernels.py -m gpu -x -q -k "uniform or random" 2>&1 | tail -2; done
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_r02j.log; cat gpurun_out/pytest_r02j.log
+python tools/stream_sweep.py gpurun_out/sweep_stream_r02 27 > gpurun_out/sweep_stream_r02.log 2>&1; grep -c . gpurun_out/sweep_stream_r02.md
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02j.json 2> gpurun_out/bench_r02j.err; tail -c 300 gpurun_out/bench_r02j.json; tail -3 gpurun_out/bench_r02j.err

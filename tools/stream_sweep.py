@@ -106,7 +106,8 @@ def sweep(log2n=27, only=None, ctx=None, pipe=None, reps=None, warm=None, verbos
             ("axpy(alpha=null)", 3, lambda: L.wk_axpy(q, tid, 1, R, Cc, None, x, Cc, n, y, Cc, n)),
             ("scal", 2, lambda: L.wk_scal(q, tid, 1, R, Cc, alpha, x, Cc, n)),
             ("hadamard (math.dot)", 3, lambda: L.wk_hadamard(q, tid, 1, R, Cc, x, Cc, n, y, Cc, n)),
-            ("sum", 1, lambda: L.wk_sum(q, tid, 1, R, Cc, n, x, hp)),
+            ("sum", 1, lambda: L.wk_sum(q, tid, 1, R, Cc, n, x, hp)),  # blocking, like math.sum: one host round trip per call
+            ("sum (device scalar)", 1, lambda: L.wk_sum_async(q, tid, 1, R, Cc, n, x, w)),  # same kernel, scalar left in HBM
             ("dot_reduce", 2, lambda: L.wk_dot_reduce(q, tid, 1, R, Cc, x, Cc, n, y, Cc, n, hp)),
             ("sin", 2, lambda: L.wk_unary(q, tid, 0, z, n)),
             ("cos", 2, lambda: L.wk_unary(q, tid, 1, z, n)),
