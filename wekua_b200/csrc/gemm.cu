@@ -14,7 +14,8 @@
 
 // cross-over of the small-tile SIMT kernel against the tensor-core kernels, in multiply-adds (measured: profiles/small_gemm_f32_r02.txt)
 #ifndef WK_SMALL_SIMT_F32
-#define WK_SMALL_SIMT_F32 7.0e7  /* ~400^3: 256^3 9.8 us against 15.9 on the tensor cores, 512^3 23.8 against 16.5 */
+#define WK_SMALL_SIMT_F32 7.0e7  /* ~400^3: 256^3 7.9 us against 15.7 on the tensor cores; twice that (512^3: 14.9 us against 16.5) where the
+                                    mid-tile cp.async kernel can take the operands (profiles/small_gemm_r02c.txt) */
 #endif
 #ifndef WK_SMALL_SIMT_F64
 #define WK_SMALL_SIMT_F64 1.4e8  /* ~512^3: 256^3 12.7 us against 42.5 on DMMA (four 128 x 128 tiles), 768^3 101 against 49 */
@@ -81,7 +82,9 @@ static int32_t gemm_any(wk_queue *q, int32_t dtype, int32_t op_a, int32_t op_b, 
     const double macs = (double)M * (double)N * (double)K;
     // (the SIMT kernel has no split-K: long-K / few-tile shapes such as 64 x 512 x 4096 stay on the tensor cores)
     const bool small_float = path == 0 && !(peers && peers->n > 1) &&
-                             ((dtype == 8 && macs <= small_f32 && K <= 512) || (dtype == 9 && macs <= small_f64 && K <= 1024));
+                             ((dtype == 8 && K <= 512 &&
+                               (macs <= small_f32 || (macs <= 2 * small_f32 && gemm_simt_mid_ok(q, dtype, op_a, op_b, M, N, K, A, lda, B, ldb)))) ||
+                              (dtype == 9 && macs <= small_f64 && K <= 1024));
     if (path != 1 && !small_float && (dtype == 8 || dtype == 9)) {
         const size_t es = dtype_size(dtype), per16 = 16 / es;
         const uint64_t a_rows = op_a ? K : M, b_rows = op_b ? N : K;
