@@ -168,3 +168,28 @@ def test_int_gemm_auto_path_matches_simt(dtype):
     np.testing.assert_array_equal(res[2], res[1])
     for t in (a, b, c):
         t.release(pipe)
+
+
+def test_int_gemm_tensor_core_inside_a_cuda_graph(tc_path):
+    """capture / replay: the byte-plane staging, every chunk launch and the workspace (allocated inside the capture on first use,
+    never freed while the graph may replay) must be graph-safe; replays with new operand contents give the new product"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    rng = np.random.default_rng(21)
+    M, N, K = 300, 260, 1100
+    for dtype in (np.int8, np.int32):
+        a, b, c = (wk.Tensor.alloc(ctx, pipe, s, dtype) for s in ((K, M), (K, N), (M, N)))
+        pipe.wait_and_cleanup()
+        pipe.begin_capture()
+        wk.blas.gemm(pipe, 3, a, 1, b, 0, None, c)
+        g = pipe.end_capture()
+        for rep in range(2):
+            ad, bd = gh.rand_data(rng, dtype, (K, M)), gh.rand_data(rng, dtype, (K, N))
+            wk.tensor.memory.read_from_buffer(pipe, a, ad)
+            wk.tensor.memory.read_from_buffer(pipe, b, bd)
+            g.launch(pipe)
+            pipe.wait_and_cleanup()
+            np.testing.assert_array_equal(gh.to_np(c), _wrap_matmul(ad, 1, bd, 0, 3, None, np.zeros((M, N), dtype)))
+        g.release()
+        for t in (a, b, c):
+            t.release(pipe)
