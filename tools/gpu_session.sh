@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi -L | head -3
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r02k_g2.json 2> gpurun_out/bench_r02k_g2.err; tail -c 600 gpurun_out/bench_r02k_g2.json; tail -3 gpurun_out/bench_r02k_g2.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -c 400
+( echo "# compute-sanitizer --tool memcheck over the GPU parity tests (all but the full-size ones), HEAD of round 2";
+  timeout 2400 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 10 python -m pytest tests/test_gpu_parity.py tests/test_gpu_int_tc.py tests/test_gpu_splitk.py tests/test_gpu_unaligned.py tests/test_gpu_simt_mid.py tests/test_gpu_complex.py tests/test_gpu_multi_tensor.py tests/test_gpu_xor.py tests/test_gpu_stream_kernels.py tests/test_gpu_linear.py -m gpu -q -k "not full_size" 2>&1 | tail -25 ) | tee gpurun_out/sanitizer_memcheck_r02.txt
