@@ -49,7 +49,7 @@ TF32_MMA_PEAK_TFLOPS = {"sustained": 903.2, "burst": 1044.9}
 # profiles/ (tools/ncu_summary.py output), matched by KERNEL NAME so a summary of an older kernel revision is not quoted
 NCU_SUMMARIES = {
     # key: (profile file, regex the "== <kernel name>" header must match)
-    "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02_n32768.txt", r"gemm_tf32x3_kernel<2, *(false|0)>"),
+    "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02m_n32768.txt", r"gemm_tf32x3_kernel<2, *(false|0), *(false|0)>"),
     "axpy_f32_2^28": ("ncu_axpy_f32_r01.txt", r"map_vec_kernel<float"),
     "axpy_f64_2^28": ("ncu_axpy_f64_r01.txt", r"map_vec_kernel<double"),
 }
