@@ -207,3 +207,21 @@ def test_f32_trig_accuracy(op):
     if op != "cos":
         z = x == 0
         assert np.array_equal(np.signbit(got[z]), np.signbit(x[z])) and np.all(got[z] == 0)
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.float32, (3000, 1000)), (np.int16, (4098, 1026)), (np.float64, (2, 1500, 700))])
+def test_memory_copy_large_dense_is_bit_exact(dtype, shape):
+    """memory.copy of >= 8 MB dense tensors runs as a streaming kernel (csrc/runtime.cu: wk_d2d -> copy_dense) instead of a
+    driver copy: every byte, padding included, must arrive; a span whose byte count is not a multiple of 16 exercises the tail"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    a = wk.Tensor.alloc(ctx, pipe, shape, dtype)
+    b = wk.Tensor.alloc(ctx, pipe, shape, dtype)
+    wk.tensor.random.uniform(pipe, a, 5)
+    before = wk.capi.launch_count()
+    wk.tensor.memory.copy(pipe, a, b)
+    assert wk.capi.launch_count() == before + 1  # a kernel, not a DMA
+    np.testing.assert_array_equal(gh.padded(b), gh.padded(a))
+    assert a.size >= 8 << 20
+    for t in (a, b):
+        t.release(pipe)

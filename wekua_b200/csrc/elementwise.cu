@@ -22,6 +22,10 @@ namespace wk {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 constexpr int kCtasPerSm = 8;
+static int env_knob(const char *name, int def) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : def;
+}
 
 template <int NP> struct Ptrs { void *p[NP]; };
 
@@ -47,6 +51,12 @@ __device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
 // vectors in flight per thread and pointer: kernels that read ONE operand from DRAM (scal, unary maps, activation
 // derivatives, fill-like) need twice the depth of the two- and three-operand kernels for the same bytes in flight
 template <typename F> struct KeepShallow : std::false_type {};  // specialised below for register-hungry FP64 maps
+// Grid size of the streaming maps.  One 32 KiB chunk per CTA and as many CTAs as the tensor has chunks beats a persistent
+// grid of 8 CTAs per SM looping over the tensor by 4-8 % on every light map (profiles/sweep_stream_grid_r02.md: f32 axpy
+// 0.97 -> 1.06 of the copy bandwidth, f64 1.08): the block scheduler evens out the SMs' progress, a persistent grid ends
+// with stragglers.  kCtasPerSm > 0 caps the grid at that many CTAs per SM: kept for the f64 maps with an IEEE division and a
+// square root per element (adagrad, rmsprop: 0.87 capped against 0.81 uncapped).  WK_MAP_CTAS_PER_SM overrides both.
+template <typename F> struct MapGridCap { static constexpr int kCtasPerSm = 0; };
 template <typename F> constexpr int unroll_for() {
     return ((F::kRead & (F::kRead - 1)) == 0 && !KeepShallow<F>::value) ? 2 * kUnroll : kUnroll;  // at most one read pointer
 }
@@ -158,7 +168,9 @@ static int32_t launch_map(wk_queue *q, Ptrs<NP> ptrs, uint64_t n, F f) {
         }
         aligned &= aligned16(ptrs.p[p]);
     }
-    const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+    static const int cap_env = env_knob("WK_MAP_CTAS_PER_SM", -1);  // (tuning knob: CTAs per SM, 0 = no cap)
+    const int ctas_per_sm = cap_env >= 0 ? cap_env : MapGridCap<F>::kCtasPerSm;
+    const uint64_t cap = ctas_per_sm > 0 ? (uint64_t)q->sm_count * ctas_per_sm : 0x7fffffffull;
     if (aligned) {
         constexpr int VEC = 16 / (int)sizeof(T);
         constexpr int kUnroll = unroll_for<F>();
@@ -341,6 +353,9 @@ template <typename T> struct RmspropF {  // rmsprop.cl:51-55
     }
 };
 
+template <> struct MapGridCap<AdagradF<double>> { static constexpr int kCtasPerSm = 8; };
+template <> struct MapGridCap<RmspropF<double>> { static constexpr int kCtasPerSm = 8; };
+
 template <typename T> struct AdamF {  // textbook Adam (Kingma & Ba alg. 1); v = {x, g, m, v}
     static constexpr unsigned kRead = 15, kWrite = 1 | 4 | 8;
     T lr, b1, b2, eps, c1, c2;  // c1 = 1/(1-b1^t), c2 = 1/(1-b2^t)
@@ -477,6 +492,7 @@ static int32_t launch_uniform_dense(wk_queue *q, T *out, uint64_t n, uint64_t se
     constexpr int VEC = 16 / (int)sizeof(T);
     const uint64_t key = (0x7C01812CF721AD1CULL ^ 0xDED46DE9839097DBULL) - seed;
     uint64_t blocks = (n / VEC + kThreads - 1) / kThreads;
+    // (persistent grid on purpose: the per-thread hash invariants are set up once per thread; uncapped measured 0.41 / 0.43)
     const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
     blocks = blocks == 0 ? 1 : (blocks > cap ? cap : blocks);
     if (n <= (1ull << 32))
@@ -737,7 +753,9 @@ static int32_t launch_mt(wk_queue *q, const wk_opt_param_t *params, uint32_t n_p
         tab.first_chunk[tab.count] = chunks;
         for (int i = tab.count + 1; i <= kMtMax; i++) tab.first_chunk[i] = chunks;
         uint64_t blocks = chunks;
-        const uint64_t cap = (uint64_t)q->sm_count * kCtasPerSm;
+        static const int cap_env = env_knob("WK_MAP_CTAS_PER_SM", -1);
+        const int ctas_per_sm = cap_env >= 0 ? cap_env : MapGridCap<F>::kCtasPerSm;
+        const uint64_t cap = ctas_per_sm > 0 ? (uint64_t)q->sm_count * ctas_per_sm : 0x7fffffffull;
         if (blocks > cap) blocks = cap;
         mt_map_kernel<T, NP, F><<<(unsigned)blocks, kThreads, 0, q->stream>>>(tab, f);
         WK_CHECK_LAUNCH();
@@ -814,6 +832,19 @@ WK_API int32_t wk_fill(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows
         return launch_map3d<scalar_t, 1>(q, p, pit, depth, rows, cols, FillF<scalar_t>{load_host<scalar_t>(scalar)});
     });
 }
+
+namespace wk {
+// memory.copy of a dense span (src/tensor/memory/copy.zig:85-98): the streaming map template with a "copy" functor --
+// 6.9 TB/s against the 6.4 TB/s of cudaMemcpyAsync device-to-device on this chip (profiles/sweep_stream_r02n.md)
+struct CopyF {
+    static constexpr unsigned kRead = 2, kWrite = 1;
+    __device__ __forceinline__ void operator()(float (&v)[2], uint64_t) const { v[0] = v[1]; }
+};
+int32_t copy_dense(wk_queue *q, void *dst, const void *src, size_t bytes) {
+    Ptrs<2> p{{dst, const_cast<void *>(src)}};
+    return launch_map<float, 2>(q, p, bytes / 4, CopyF{});
+}
+}  // namespace wk
 
 WK_API int32_t wk_uniform(wk_queue *q, int32_t dtype, uint64_t depth, uint64_t rows, uint64_t cols, void *buf, uint64_t rp,
                           uint64_t sp, uint64_t seed, const void *minp, const void *maxp) {
@@ -911,7 +942,8 @@ WK_API int32_t wk_bias_add(wk_queue *q, int32_t dtype, void *output, const void 
             return WK_ERR_INVALID_VALUE;
         }
         uint64_t blocks = (n_units + (uint64_t)kThreads * kBiasUnroll - 1) / ((uint64_t)kThreads * kBiasUnroll);
-        const uint64_t cap = (uint64_t)q->sm_count * 4;
+        static const int bias_ctas = env_knob("WK_BIAS_CTAS_PER_SM", 0);  // 0 = one chunk per CTA (f32 0.94 -> 1.03; see MapGridCap)
+        const uint64_t cap = bias_ctas > 0 ? (uint64_t)q->sm_count * bias_ctas : 0x7fffffffull;
         if (blocks > cap) blocks = cap;
         if (vec)
             bias_add_kernel<scalar_t, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,
@@ -934,7 +966,8 @@ int32_t bias_act(wk_queue *q, int32_t dtype, void *output, const void *bias, uin
         if (n_units == 0) return WK_OK;
         if (rp_units >= (1ull << 31)) return WK_ERR_INVALID_VALUE;
         uint64_t blocks = (n_units + (uint64_t)kThreads * kBiasUnroll - 1) / ((uint64_t)kThreads * kBiasUnroll);
-        const uint64_t cap = (uint64_t)q->sm_count * 4;
+        static const int bias_ctas = env_knob("WK_BIAS_CTAS_PER_SM", 0);  // 0 = one chunk per CTA (f32 0.94 -> 1.03; see MapGridCap)
+        const uint64_t cap = bias_ctas > 0 ? (uint64_t)q->sm_count * bias_ctas : 0x7fffffffull;
         if (blocks > cap) blocks = cap;
         if (vec)
             bias_add_kernel<scalar_t, true, true><<<(unsigned)blocks, kThreads, 0, q->stream>>>((scalar_t *)output, (const scalar_t *)bias,

@@ -467,6 +467,16 @@ WK_API int32_t wk_d2h_rect(wk_queue *q, void *dst_host, const void *src, size_t 
 WK_API int32_t wk_d2d(wk_queue *q, void *dst, const void *src, size_t bytes) {
     WK_CHECK_QUEUE(q);
     if (!dst || !src) return WK_ERR_INVALID_BUFFER;
+    // Large aligned spans inside THIS device's memory stream through the map kernel (faster than the driver's copy, and an
+    // ordinary kernel node in graphs).  Anything that touches a peer (IPC-mapped buffers: the B shares of rowshard) stays on
+    // the copy engines, which is the point of those pushes.
+    if (bytes >= (8u << 20) && bytes % 4 == 0 && aligned16(dst) && aligned16(src)) {
+        cudaPointerAttributes ad{}, as{};
+        if (cudaPointerGetAttributes(&ad, dst) == cudaSuccess && cudaPointerGetAttributes(&as, src) == cudaSuccess &&
+            ad.type == cudaMemoryTypeDevice && as.type == cudaMemoryTypeDevice && ad.device == q->device && as.device == q->device)
+            return wk::copy_dense(q, dst, src, bytes);  // (counts itself as a launch)
+        cudaGetLastError();
+    }
     WK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, q->stream));
     return WK_OK;
 }
