@@ -225,3 +225,35 @@ def test_memory_copy_large_dense_is_bit_exact(dtype, shape):
     assert a.size >= 8 << 20
     for t in (a, b):
         t.release(pipe)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_large_sum_and_dot_use_chunk_scheduled_reduction(dtype):
+    """>= 37 MB dense inputs take the dynamically scheduled one-launch reduction (csrc/reduce.cu: reduce_dense_dyn_kernel): the
+    value must not depend on which CTA summed which chunk -- repeated calls are bit-identical -- integers are exact (mod 2^32),
+    floats agree with a float64 sum within n * eps * sum|x|"""
+    wk = gh.wk()
+    ctx, pipe = gh.ctx_pipe()
+    shape = (4096, 12290)  # 201 MB f32 / 403 MB f64; cols % 4 == 2
+    x = wk.Tensor.alloc(ctx, pipe, shape, dtype)
+    y = wk.Tensor.alloc(ctx, pipe, shape, dtype)
+    wk.tensor.random.uniform(pipe, x, 3, -1, 1) if np.dtype(dtype).kind == "f" else wk.tensor.random.uniform(pipe, x, 3)
+    wk.tensor.random.uniform(pipe, y, 4, -1, 1) if np.dtype(dtype).kind == "f" else wk.tensor.random.uniform(pipe, y, 4)
+    xh, yh = gh.to_np(x), gh.to_np(y)
+    sums = [wk.math.sum(pipe, x) for _ in range(4)]
+    dots = [wk.blas.dot_reduce(pipe, x, y) for _ in range(4)]
+    assert all(np.array_equal(np.asarray(s), np.asarray(sums[0])) for s in sums)
+    assert all(np.array_equal(np.asarray(d), np.asarray(dots[0])) for d in dots)
+    if np.dtype(dtype).kind == "i":
+        assert np.int32(sums[0]) == xh.astype(np.int64).sum().astype(np.int32)
+        with np.errstate(over="ignore"):
+            assert np.int32(dots[0]) == (xh.astype(np.int64) * yh.astype(np.int64)).sum().astype(np.int32)
+    else:
+        eps = np.finfo(dtype).eps
+        n = xh.size
+        want_s, want_d = xh.astype(np.float64).sum(), (xh.astype(np.float64) * yh.astype(np.float64)).sum()
+        # tree summation (4 accumulators x 256 threads per chunk, chunk partials, final tree): worst case log2(n) * eps * sum|.|
+        assert abs(float(sums[0]) - want_s) <= 32 * eps * np.abs(xh).astype(np.float64).sum()
+        assert abs(float(dots[0]) - want_d) <= 32 * eps * np.abs(xh.astype(np.float64) * yh.astype(np.float64)).sum()
+    for t in (x, y):
+        t.release(pipe)

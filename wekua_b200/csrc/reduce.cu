@@ -128,6 +128,76 @@ __global__ void __launch_bounds__(kRThreads) reduce_runs_kernel(const T *__restr
     }
 }
 
+// Dense, vectorisable, LARGE inputs: the same one-launch reduction, but the unit of work is a 512 KiB chunk that persistent
+// CTAs fetch from a counter as they go, and the partial sums are indexed by CHUNK, not by CTA.  A statically partitioned
+// persistent grid ends with stragglers (the SMs do not get equal shares of the HBM bandwidth: the streaming maps gained 4-9 %
+// from finer scheduling, profiles/sweep_stream_grid_r02.md); with chunk-indexed partials the value still does not depend on
+// which CTA summed which chunk -- every chunk is summed by the same thread/shuffle tree, the last CTA folds the chunk partials
+// in index order.
+constexpr int kDynChunkVecs = 32768;  // 16-byte vectors per chunk (512 KiB): 128 per thread
+template <typename T, int NIN>
+__global__ void __launch_bounds__(kRThreads) reduce_dense_dyn_kernel(const T *__restrict__ x, const T *__restrict__ y, uint64_t nv,
+                                                                     unsigned n_chunks, typename Acc<T>::type *partial,
+                                                                     unsigned *ticket, T *__restrict__ out, unsigned *posted,
+                                                                     unsigned seq) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    union Pack { uint4 u; T e[VEC]; };
+    const uint4 *xv = reinterpret_cast<const uint4 *>(x);
+    const uint4 *yv = reinterpret_cast<const uint4 *>(y);
+    __shared__ unsigned s_next;
+    unsigned c = blockIdx.x;  // the first chunk is static, the rest come from ticket[1]
+    while (c < n_chunks) {
+        if (threadIdx.x == 0) s_next = gridDim.x + atomicAdd(ticket + 1, 1u);
+        A acc[4] = {AccZero<A>::get(), AccZero<A>::get(), AccZero<A>::get(), AccZero<A>::get()};
+        const uint64_t v0 = (uint64_t)c * kDynChunkVecs + threadIdx.x;
+#pragma unroll 2
+        for (int k = 0; k < kDynChunkVecs / kRThreads; k += 4) {
+            Pack px[4], py[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint64_t i = v0 + (uint64_t)(k + u) * kRThreads;
+                px[u].u = make_uint4(0u, 0u, 0u, 0u);
+                if (NIN == 2) py[u].u = make_uint4(0u, 0u, 0u, 0u);
+                if (i < nv) {
+                    px[u].u = __ldg(xv + i);
+                    if (NIN == 2) py[u].u = __ldg(yv + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int e = 0; e < VEC; e++)
+                    acc[u] = acc[u] + (NIN == 2 ? to_acc<T>(px[u].e[e]) * to_acc<T>(py[u].e[e]) : to_acc<T>(px[u].e[e]));
+        }
+        A v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        v = block_reduce_sum<A>(v);
+        if (threadIdx.x == 0) partial[c] = v;
+        c = s_next;
+        __syncthreads();  // everybody has read s_next before thread 0 draws the next one
+    }
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    A f = AccZero<A>::get();
+    for (unsigned i = threadIdx.x; i < n_chunks; i += kRThreads) f = f + ld_cg_acc(partial + i);
+    f = block_reduce_sum<A>(f);
+    if (threadIdx.x == 0) {
+        *out = from_acc<T>(f);
+        ticket[0] = 0;
+        ticket[1] = 0;
+        if (posted) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(posted) = seq;
+        }
+    }
+}
+
 template <typename T, int NIN>
 static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, uint64_t rows, uint64_t run_len, uint64_t xrp,
                            uint64_t xsp, uint64_t yrp, uint64_t ysp, void *host_out, void *device_out = nullptr) {
@@ -159,7 +229,15 @@ static int32_t reduce_runs(wk_queue *q, const T *x, const T *y, uint64_t depth, 
     unsigned *posted = device_out ? nullptr : reinterpret_cast<unsigned *>((char *)q->pinned + 128);
     const unsigned seq = device_out ? 0 : ++q->reduce_seq;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    if (vec)
+    const uint64_t nv = run_len / VEC, n_chunks = (nv + kDynChunkVecs - 1) / kDynChunkVecs;
+    static const int dyn_env = getenv("WK_REDUCE_DYNAMIC") ? atoi(getenv("WK_REDUCE_DYNAMIC")) : 1;
+    if (dyn_env && vec && n_runs == 1 && n_chunks >= 2 * (uint64_t)q->sm_count && n_chunks < 0x7fffffffull) {
+        rc = ensure_scratch(q, n_chunks * sizeof(A) + 64);
+        if (rc != WK_OK) return rc;
+        partial = reinterpret_cast<A *>((char *)q->scratch + 64);
+        reduce_dense_dyn_kernel<T, NIN><<<(unsigned)cap, kRThreads, 0, q->stream>>>(x, y, nv, (unsigned)n_chunks, partial, q->reduce_ticket,
+                                                                                   result, posted, seq);
+    } else if (vec)
         reduce_runs_kernel<T, NIN, true><<<grid, kRThreads, 0, q->stream>>>(x, y, run_len, n_runs, rows, xrp, xsp, yrp, ysp, partial,
                                                                            q->reduce_ticket, result, posted, seq);
     else
