@@ -50,16 +50,20 @@ __device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
 //                 __device__ void operator()(T (&v)[NP], uint64_t idx) const   (idx = element index)
 // vectors in flight per thread and pointer: kernels that read ONE operand from DRAM (scal, unary maps, activation
 // derivatives, fill-like) need twice the depth of the two- and three-operand kernels for the same bytes in flight
-template <typename F> struct KeepShallow : std::false_type {};  // specialised below for register-hungry FP64 maps
-// Grid size of the streaming maps.  One 32 KiB chunk per CTA and as many CTAs as the tensor has chunks beats a persistent
+// Grid size of the streaming maps.  One chunk (kThreads x MapUnroll vectors per pointer: 16 KiB) per CTA and as many CTAs as
+// the tensor has chunks beats a persistent
 // grid of 8 CTAs per SM looping over the tensor by 4-8 % on every light map (profiles/sweep_stream_grid_r02.md: f32 axpy
 // 0.97 -> 1.06 of the copy bandwidth, f64 1.08): the block scheduler evens out the SMs' progress, a persistent grid ends
 // with stragglers.  kCtasPerSm > 0 caps the grid at that many CTAs per SM: kept for the f64 maps with an IEEE division and a
 // square root per element (adagrad, rmsprop: 0.87 capped against 0.81 uncapped).  WK_MAP_CTAS_PER_SM overrides both.
 template <typename F> struct MapGridCap { static constexpr int kCtasPerSm = 0; };
-template <typename F> constexpr int unroll_for() {
-    return ((F::kRead & (F::kRead - 1)) == 0 && !KeepShallow<F>::value) ? 2 * kUnroll : kUnroll;  // at most one read pointer
-}
+// Vectors in flight per thread and pointer (a CTA's chunk is kThreads x this many 16-byte vectors).  With one chunk per CTA
+// the memory system is kept busy by the NUMBER of CTAs, so depth beyond 4 only costs registers (round 1 doubled it for
+// one-pointer maps under its persistent grid): 4 instead of 8 lifts the unary maps by up to 12 % (f32 sin 0.94 -> 1.02,
+// tan 0.92 -> 1.01; f64 cosh 0.94 -> 1.05, sigmoid 0.92 -> 1.03).  The register-hungriest multi-pointer maps take 2
+// (specialisations next to the functors; profiles/sweep_stream_grid_r02.md).
+template <typename F> struct MapUnroll { static constexpr int value = kUnroll; };
+template <typename F> constexpr int unroll_for() { return MapUnroll<F>::value; }
 
 template <typename T, int NP, typename F>
 __global__ void __launch_bounds__(kThreads) map_vec_kernel(Ptrs<NP> ptrs, uint64_t n, F f) {
@@ -276,7 +280,7 @@ template <typename T, int OP> struct UnaryF {  // trig.cl:3-67, sigmoid.cl:14-15
 };
 
 // (libdevice's f64 tan / tanh / cosh and the IEEE division of sigmoid were issue-bound here -- 0.70 / 0.65 / 0.86 / 0.84 of the
-// copy bandwidth -- until they got the branch-free constant-bank implementations of common.cuh; no map needs KeepShallow now.)
+// copy bandwidth -- until they got the branch-free constant-bank implementations of common.cuh.)
 
 template <typename BT, int OP> struct UnaryF<Cx<BT>, OP> {  // trig.cl:5-66, complex branches
     static constexpr unsigned kRead = 1, kWrite = 1;
@@ -321,6 +325,8 @@ template <typename T, bool DEV> struct MseF {  // mse.cl:28-33: v = {output, exp
     }
 };
 
+template <> struct MapUnroll<MseF<double, false>> { static constexpr int value = 2; };  // 1.02 -> 1.07
+
 template <typename T> struct GdmF {  // gdm.cl:28-31: v = {x, g, velocity}
     static constexpr unsigned kRead = 7, kWrite = 5;
     T lr, beta;
@@ -353,6 +359,9 @@ template <typename T> struct RmspropF {  // rmsprop.cl:51-55
     }
 };
 
+template <> struct MapUnroll<GdmF<double>> { static constexpr int value = 2; };      // 0.96 -> 1.07
+template <> struct MapUnroll<AdagradF<double>> { static constexpr int value = 2; };  // 0.89 -> 0.94
+template <> struct MapUnroll<RmspropF<double>> { static constexpr int value = 2; };  // 0.89 -> 0.95
 template <> struct MapGridCap<AdagradF<double>> { static constexpr int kCtasPerSm = 8; };
 template <> struct MapGridCap<RmspropF<double>> { static constexpr int kCtasPerSm = 8; };
 
@@ -368,6 +377,8 @@ template <typename T> struct AdamF {  // textbook Adam (Kingma & Ba alg. 1); v =
         v[3] = s;
     }
 };
+
+template <> struct MapUnroll<AdamF<float>> { static constexpr int value = 2; };  // 0.96 -> 1.05 (f64: 0.99 at 4, 0.94 at 2)
 
 // uniform.cl:32-54 (little-endian branch; `seed2 << 32` is always 0; `*` binds tighter than `^`), spelled out on 32-bit
 // halves.  The hash is the whole cost of the kernel (an f32 element is 4 bytes of HBM against ~25 integer instructions, and
