@@ -54,8 +54,9 @@ __device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
 // the tensor has chunks beats a persistent
 // grid of 8 CTAs per SM looping over the tensor by 4-8 % on every light map (profiles/sweep_stream_grid_r02.md: f32 axpy
 // 0.97 -> 1.06 of the copy bandwidth, f64 1.08): the block scheduler evens out the SMs' progress, a persistent grid ends
-// with stragglers.  kCtasPerSm > 0 caps the grid at that many CTAs per SM: kept for the f64 maps with an IEEE division and a
-// square root per element (adagrad, rmsprop: 0.87 capped against 0.81 uncapped).  WK_MAP_CTAS_PER_SM overrides both.
+// with stragglers.  kCtasPerSm > 0 would cap the grid at that many CTAs per SM for a functor (none needs it: the f64 adagrad /
+// rmsprop maps that lost without a cap at 4 vectors per thread gain at 2: 0.94 / 0.97 capped, 1.07 / 1.06 uncapped).
+// WK_MAP_CTAS_PER_SM overrides.
 template <typename F> struct MapGridCap { static constexpr int kCtasPerSm = 0; };
 // Vectors in flight per thread and pointer (a CTA's chunk is kThreads x this many 16-byte vectors).  With one chunk per CTA
 // the memory system is kept busy by the NUMBER of CTAs, so depth beyond 4 only costs registers (round 1 doubled it for
@@ -360,10 +361,8 @@ template <typename T> struct RmspropF {  // rmsprop.cl:51-55
 };
 
 template <> struct MapUnroll<GdmF<double>> { static constexpr int value = 2; };      // 0.96 -> 1.07
-template <> struct MapUnroll<AdagradF<double>> { static constexpr int value = 2; };  // 0.89 -> 0.94
-template <> struct MapUnroll<RmspropF<double>> { static constexpr int value = 2; };  // 0.89 -> 0.95
-template <> struct MapGridCap<AdagradF<double>> { static constexpr int kCtasPerSm = 8; };
-template <> struct MapGridCap<RmspropF<double>> { static constexpr int kCtasPerSm = 8; };
+template <> struct MapUnroll<AdagradF<double>> { static constexpr int value = 2; };  // 0.89 -> 1.07
+template <> struct MapUnroll<RmspropF<double>> { static constexpr int value = 2; };  // 0.89 -> 1.06
 
 template <typename T> struct AdamF {  // textbook Adam (Kingma & Ba alg. 1); v = {x, g, m, v}
     static constexpr unsigned kRead = 15, kWrite = 1 | 4 | 8;
@@ -520,7 +519,7 @@ static int32_t launch_uniform_dense(wk_queue *q, T *out, uint64_t n, uint64_t se
 // vectors incrementally -- one modulo before the loop, an add and a conditional subtract per step -- and reads bias
 // through L1 at the point of use.  VECTOR = false is the same loop over single elements (row pitch or n not a
 // multiple of the vector width).  rp_units < 2^32 (host-checked).
-constexpr int kBiasUnroll = 8;
+constexpr int kBiasUnroll = 4;  // (8 under round 1's capped grid; with one chunk per CTA 4 is faster: f64 1.00 -> 1.06)
 template <typename T> __device__ __forceinline__ T bias_act_apply(T v, int) { return v; }
 template <> __device__ __forceinline__ float bias_act_apply<float>(float v, int act) {
     return act == WK_ACT_SIGMOID ? wk_sigmoid(v) : act == WK_ACT_TANH ? wk_tanh(v) : v;
