@@ -58,6 +58,8 @@ __device__ __forceinline__ void st_na(uint4 *p, const uint4 &v) {
 // rmsprop maps that lost without a cap at 4 vectors per thread gain at 2: 0.94 / 0.97 capped, 1.07 / 1.06 uncapped).
 // WK_MAP_CTAS_PER_SM overrides.
 template <typename F> struct MapGridCap { static constexpr int kCtasPerSm = 0; };
+// the multi-tensor kernel keeps 4 vectors per thread for every functor, so there the two f64 maps keep their cap (below)
+template <typename F> struct MtGridCap { static constexpr int kCtasPerSm = 0; };
 // Vectors in flight per thread and pointer (a CTA's chunk is kThreads x this many 16-byte vectors).  With one chunk per CTA
 // the memory system is kept busy by the NUMBER of CTAs, so depth beyond 4 only costs registers (round 1 doubled it for
 // one-pointer maps under its persistent grid): 4 instead of 8 lifts the unary maps by up to 12 % (f32 sin 0.94 -> 1.02,
@@ -361,6 +363,8 @@ template <typename T> struct RmspropF {  // rmsprop.cl:51-55
 };
 
 template <> struct MapUnroll<GdmF<double>> { static constexpr int value = 2; };      // 0.96 -> 1.07
+template <> struct MtGridCap<AdagradF<double>> { static constexpr int kCtasPerSm = 8; };  // (0.87 capped, 0.81 uncapped at 4 vectors)
+template <> struct MtGridCap<RmspropF<double>> { static constexpr int kCtasPerSm = 8; };
 template <> struct MapUnroll<AdagradF<double>> { static constexpr int value = 2; };  // 0.89 -> 1.07
 template <> struct MapUnroll<RmspropF<double>> { static constexpr int value = 2; };  // 0.89 -> 1.06
 
@@ -764,7 +768,7 @@ static int32_t launch_mt(wk_queue *q, const wk_opt_param_t *params, uint32_t n_p
         for (int i = tab.count + 1; i <= kMtMax; i++) tab.first_chunk[i] = chunks;
         uint64_t blocks = chunks;
         static const int cap_env = env_knob("WK_MAP_CTAS_PER_SM", -1);
-        const int ctas_per_sm = cap_env >= 0 ? cap_env : MapGridCap<F>::kCtasPerSm;
+        const int ctas_per_sm = cap_env >= 0 ? cap_env : MtGridCap<F>::kCtasPerSm;
         const uint64_t cap = ctas_per_sm > 0 ? (uint64_t)q->sm_count * ctas_per_sm : 0x7fffffffull;
         if (blocks > cap) blocks = cap;
         mt_map_kernel<T, NP, F><<<(unsigned)blocks, kThreads, 0, q->stream>>>(tab, f);
