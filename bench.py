@@ -50,8 +50,8 @@ TF32_MMA_PEAK_TFLOPS = {"sustained": 903.2, "burst": 1044.9}
 NCU_SUMMARIES = {
     # key: (profile file, regex the "== <kernel name>" header must match)
     "gemm_f32_n32768_1gpu": ("ncu_gemm_f32_r02m_n32768.txt", r"gemm_tf32x3_kernel<2, *(false|0), *(false|0)>"),
-    "axpy_f32_2^28": ("ncu_axpy_f32_r01.txt", r"map_vec_kernel<float"),
-    "axpy_f64_2^28": ("ncu_axpy_f64_r01.txt", r"map_vec_kernel<double"),
+    "axpy_f32_2^28": ("ncu_axpy_f32_r02q.txt", r"map_vec_kernel<float, *2, *AxpyF"),
+    "axpy_f64_2^28": ("ncu_axpy_f64_r02q.txt", r"map_vec_kernel<double, *2, *AxpyF"),
 }
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
